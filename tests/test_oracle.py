@@ -1,0 +1,217 @@
+"""CPU tests: the oracle restatements against the golden fixtures produced by the
+live reference (tests/golden/make_golden.py).  Tolerances are float64 round-off."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_grads_close, flat, grads_from, load_golden, net_from
+from oracle import autograd_ref as AR
+from oracle import jets_numpy as O
+
+TOL = 1e-11
+
+POISSON = [
+    ("poisson_pinn_d1_w64_fbc", "pinn", "FBC"), ("poisson_pinn_d3_w64_fbc", "pinn", "FBC"),
+    ("poisson_drm_d5_w64_rb", "drm", "RB"), ("poisson_pinn_d2_w16_fbc", "pinn", "FBC"),
+    ("poisson_pinn_d5_w16_fbc", "pinn", "FBC"), ("poisson_pinn_d3_w16_rb", "pinn", "RB"),
+    ("poisson_pinn_d4_w12_fbc", "pinn", "FBC"), ("poisson_drm_d1_w16_fbc", "drm", "FBC"),
+    ("poisson_drm_d2_w16_fbc", "drm", "FBC"), ("poisson_drm_d3_w16_fbc", "drm", "FBC"),
+]
+
+
+@pytest.mark.parametrize("name,method,bc", POISSON)
+def test_numpy_oracle_poisson(name, method, bc):
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    fn = O.poisson_pinn_loss if method == "pinn" else O.poisson_drm_loss
+    loss, gWs, gbs = fn(Ws, bs, g["X"], g["f"], float(g["L"]), bc)
+    assert abs(loss - g["loss"]) <= TOL * max(1.0, abs(g["loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g), TOL, name)
+
+
+@pytest.mark.parametrize("name,method,bc", POISSON)
+def test_numpy_oracle_jets(name, method, bc):
+    """u, grad u and Laplacian from the jets equal the reference helpers' outputs."""
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    X = g["X"]; d = X.shape[1]
+    J, _ = O.mlp_jets_forward(Ws, bs, X, O.SIN, 2)
+    U, _ = O.apply_envelope(J, X, 2, O.ENV_POLY if bc == "FBC" else O.ENV_NONE, 0.0, float(g["L"]))
+    np.testing.assert_allclose(U[:, 0:1], g["u"], rtol=0, atol=TOL * max(1, np.abs(g["u"]).max()))
+    np.testing.assert_allclose(U[:, 1:1 + d], g["grad_u"], rtol=0, atol=TOL * max(1, np.abs(g["grad_u"]).max()))
+    np.testing.assert_allclose(U[:, 1 + d:].sum(1, keepdims=True), g["lap_u"], rtol=0, atol=TOL * max(1, np.abs(g["lap_u"]).max()))
+
+
+@pytest.mark.parametrize("name,method,bc", POISSON[:6])
+def test_autograd_port_poisson(name, method, bc):
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    widths = [Ws[0].shape[1]] + [W.shape[0] for W in Ws]
+    net = AR.build_mlp(widths, "sin", torch.float64)
+    AR.load_params(net, Ws, bs)
+    X = torch.tensor(g["X"]); f = torch.tensor(g["f"])
+    loss, gflat = AR.loss_and_grads(method, net, X, f, float(g["L"]), bc)
+    assert abs(loss - g["loss"]) <= TOL * max(1.0, abs(g["loss"]))
+    want = flat(*grads_from(g))
+    assert np.max(np.abs(gflat.numpy() - want)) <= TOL * np.max(np.abs(want))
+    # chunked accumulation (how the CPU baseline handles 2^22 points) is exact for plain means
+    loss2, g2 = AR.loss_and_grads(method, net, X, f, float(g["L"]), bc, chunk=17)
+    assert abs(loss2 - g["loss"]) <= 1e-10 * max(1.0, abs(g["loss"]))
+    assert np.max(np.abs(g2.numpy() - want)) <= 1e-10 * np.max(np.abs(want))
+
+
+def test_network_free_known_answer():
+    """-Δu* == f for the manufactured solution (Poisson_ND.py:49-58): pins the rhs helper."""
+    torch.manual_seed(3)
+    L, ks = 2.0, [1, 2, 3]
+    X = (torch.rand(200, 3, dtype=torch.float64) * L).requires_grad_(True)
+    u = torch.ones(200, 1, dtype=torch.float64)
+    for i, k in enumerate(ks):
+        u = u * torch.sin(k * math.pi * X[:, i:i + 1] / L)
+    lap = AR._laplace(u, X)
+    assert (-lap - AR.manufactured_rhs(X, L, ks)).abs().max().item() < 5e-12
+
+
+def _wan_check(g, u_net, v_net, X, f, lo, hi, a, beta, E, eps_den):
+    return O.wan_means(u_net, v_net, X, f, lo, hi, a=a, beta=beta, E=E, eps_den=eps_den)
+
+
+def _combine(G, coefs):
+    gW = [sum(c * G[j][0][i] for j, c in enumerate(coefs)) for i in range(len(G[0][0]))]
+    gb = [sum(c * G[j][1][i] for j, c in enumerate(coefs)) for i in range(len(G[0][1]))]
+    return gW, gb
+
+
+def test_numpy_oracle_poisson_wan():
+    g = load_golden("poisson_wan_d2_w16")
+    L = float(g["L"]); eps = 1e-8; reg = float(g["v_reg_weight"])
+    uW, ub = net_from(g, "u_"); vW, vb = net_from(g, "v_")
+    u_net = dict(Ws=uW, bs=ub, act=O.SIN, env=dict(kind=O.ENV_POLY, lo=0.0, hi=L))
+    v_net = dict(Ws=vW, bs=vb, act=O.SIN, env=dict(kind=O.ENV_NONE))
+    m, Gu, Gv, _ = O.wan_means(u_net, v_net, g["X"], g["f"], 0.0, L, a=1.0)
+    m1, m2, m3, m4 = m
+    loss_u = m1 * m1 / (m2 + eps)
+    loss_v = -math.log(loss_u + eps) + reg * m4
+    assert abs(m1 - g["weak"]) <= TOL and abs(m2 - g["phi_norm"]) <= TOL
+    assert abs(loss_u - g["loss_u"]) <= TOL * max(1, abs(g["loss_u"]))
+    assert abs(loss_v - g["loss_v"]) <= TOL * max(1, abs(g["loss_v"]))
+    dlu = [2 * m1 / (m2 + eps), -m1 * m1 / (m2 + eps) ** 2, 0.0, 0.0]
+    k = -1.0 / (loss_u + eps)
+    dlv = [k * dlu[0], k * dlu[1], 0.0, reg]
+    assert_grads_close(_combine(Gu, dlu), grads_from(g, "lu_u_"), 1e-10, "lu/u")
+    assert_grads_close(_combine(Gv, dlu), grads_from(g, "lu_v_"), 1e-10, "lu/v")
+    assert_grads_close(_combine(Gu, dlv), grads_from(g, "lv_u_"), 1e-10, "lv/u")
+    assert_grads_close(_combine(Gv, dlv), grads_from(g, "lv_v_"), 1e-10, "lv/v")
+
+
+@pytest.mark.parametrize("name", ["ipw1d_fbc_n2", "ipw1d_fn_n3"])
+def test_numpy_oracle_ipw1d(name):
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    L = float(g["L"]); n = int(g["n"]); X = g["x"]
+    # the reference stores node positions as float32 tensors (IPW_1D_PINN_DRM.py:38-40)
+    nodes = [[float(np.float32(k * L / n)) for k in range(1, n)]] if name.endswith("fn_n3") else None
+    env = dict(kind=O.ENV_POLY, lo=0.0, hi=L, nodes=nodes)
+    k2 = (n * math.pi / L) ** 2
+    loss, gWs, gbs, _ = O.eigen_pinn_loss(Ws, bs, X, O.TANH, env, alpha=1.0, beta=k2, E=0.0)
+    assert abs(loss - g["pinn_loss"]) <= 1e-10 * max(1, abs(g["pinn_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "pinn_"), 1e-9, name + " pinn")
+    loss, gWs, gbs, _ = O.rayleigh_loss(Ws, bs, X, O.TANH, env, a=1.0, beta=None)
+    assert abs(loss - g["drm_loss"]) <= 1e-10 * max(1, abs(g["drm_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "drm_"), 1e-9, name + " drm")
+
+
+def test_numpy_oracle_ipw1d_wan():
+    g = load_golden("ipw1d_wan_n2")
+    L = float(g["L"]); n = int(g["n"]); X = g["x"]
+    uW, ub = net_from(g, "u_"); vW, vb = net_from(g, "v_")
+    u_net = dict(Ws=uW, bs=ub, act=O.TANH, env=dict(kind=O.ENV_POLY, lo=0.0, hi=L))
+    v_net = dict(Ws=vW, bs=vb, act=O.TANH, env=dict(kind=O.ENV_NONE))
+    E = (n * math.pi) ** 2 / (2 * L * L)
+    m, Gu, Gv, _ = O.wan_means(u_net, v_net, X, None, 0.0, L, a=0.5, beta=None, E=E)
+    m1, m2, m3, _ = m
+    lpde = m1 * m1 / (m2 + 1e-8)
+    lnorm = (L * m3 - 1.0) ** 2
+    assert abs(lpde - g["loss_pde"]) <= 1e-10 * max(1, abs(g["loss_pde"]))
+    assert abs(lnorm - g["loss_norm"]) <= 1e-10 * max(1, abs(g["loss_norm"]))
+    dtot = [2 * m1 / (m2 + 1e-8), -m1 * m1 / (m2 + 1e-8) ** 2, 2 * (L * m3 - 1.0) * L, 0.0]
+    k = -1.0 / (lpde + 1e-8)
+    dlv = [k * dtot[0], k * dtot[1], 0.0, 0.0]
+    assert_grads_close(_combine(Gu, dtot), grads_from(g, "tot_u_"), 1e-9, "tot/u")
+    assert_grads_close(_combine(Gv, dtot), grads_from(g, "tot_v_"), 1e-9, "tot/v")
+    assert_grads_close(_combine(Gu, dlv), grads_from(g, "lv_u_"), 1e-9, "lv/u")
+    assert_grads_close(_combine(Gv, dlv), grads_from(g, "lv_v_"), 1e-9, "lv/v")
+
+
+@pytest.mark.parametrize("name", ["qho2d_fbc_00", "qho2d_fn_21"])
+def test_numpy_oracle_qho2d(name):
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    L = float(g["L"]); E = float(g["E"])
+    X = np.stack([g["x"].reshape(-1), g["y"].reshape(-1)], axis=1)
+    nodes = [list(g["nodes_x"]), list(g["nodes_y"])] if "fn" in name else None
+    env = dict(kind=O.ENV_EXPWIN, lo=-L, hi=L, nodes=nodes)
+    V = 0.5 * math.sqrt(2) ** 2 * (X[:, 0:1] ** 2 + X[:, 1:2] ** 2)
+    J, _ = O.mlp_jets_forward(Ws, bs, X, O.SIN, 0)
+    U, _ = O.apply_envelope(J, X, 0, env["kind"], -L, L, nodes)
+    np.testing.assert_allclose(U.reshape(g["u"].shape), g["u"], rtol=0, atol=1e-11 * max(1, np.abs(g["u"]).max()))
+    loss, gWs, gbs, _ = O.eigen_pinn_loss(Ws, bs, X, O.SIN, env, alpha=-0.5, beta=V, E=E)
+    assert abs(loss - g["pinn_loss"]) <= 1e-10 * max(1, abs(g["pinn_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "pinn_"), 1e-9, name + " pinn")
+    loss, gWs, gbs, _ = O.rayleigh_loss(Ws, bs, X, O.SIN, env, a=0.5, beta=V, eps_in=1e-8)
+    assert abs(loss - g["drm_loss"]) <= 1e-10 * max(1, abs(g["drm_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "drm_"), 1e-9, name + " drm")
+
+
+def test_numpy_oracle_qho2d_wan():
+    g = load_golden("qho2d_wan_10")
+    L = float(g["L"]); E = float(g["E"])
+    X = np.stack([g["x"].reshape(-1), g["y"].reshape(-1)], axis=1)
+    uW, ub = net_from(g, "u_"); vW, vb = net_from(g, "v_")
+    env = dict(kind=O.ENV_EXPWIN, lo=-L, hi=L)
+    u_net = dict(Ws=uW, bs=ub, act=O.SIN, env=env)
+    v_net = dict(Ws=vW, bs=vb, act=O.SIN, env=env)
+    V = 0.5 * math.sqrt(2) ** 2 * (X[:, 0:1] ** 2 + X[:, 1:2] ** 2)
+    m, Gu, Gv, _ = O.wan_means(u_net, v_net, X, None, -L, L, a=0.5, beta=V, E=E, eps_den=1e-10)
+    m1, m2, m3, _ = m
+    lpde = m1 * m1 / (m2 + 1e-8)
+    lnorm = (4 * L * L * m3 - 1.0) ** 2
+    assert abs(lpde - g["loss_pde"]) <= 1e-9 * max(1, abs(g["loss_pde"]))
+    assert abs(lnorm - g["loss_norm"]) <= 1e-9 * max(1, abs(g["loss_norm"]))
+    dtot = [2 * m1 / (m2 + 1e-8), -m1 * m1 / (m2 + 1e-8) ** 2, 2 * (4 * L * L * m3 - 1.0) * 4 * L * L, 0.0]
+    assert_grads_close(_combine(Gu, dtot), grads_from(g, "tot_u_"), 1e-8, "tot/u")
+    assert_grads_close(_combine(Gv, dtot), grads_from(g, "tot_v_"), 1e-8, "tot/v")
+
+
+@pytest.mark.parametrize("name,kind", [("kh1d_raw", O.ENV_NONE), ("kh1d_fbc", O.ENV_EXPWIN)])
+def test_numpy_oracle_kh1d(name, kind):
+    g = load_golden(name)
+    L = float(g["L"]); E = float(g["E"])
+    X = g["x"].reshape(-1, 1); V = g["V"].reshape(-1, 1)
+    uW, ub = net_from(g, "u_"); vW, vb = net_from(g, "v_")
+    # pinn_loss uses L_here = max|x| (KH_1D.py:227) which equals L on this grid
+    env = dict(kind=kind, lo=-L, hi=L)
+    loss, gWs, gbs, dE = O.eigen_pinn_loss(uW, ub, X, O.SIN, env, alpha=-0.5, beta=V, E=E)
+    assert abs(loss - g["pinn_loss"]) <= 1e-10 * max(1, abs(g["pinn_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "pinn_"), 1e-9, name + " pinn")
+    assert abs(dE - float(g["pinn_gE"])) <= 1e-9 * max(1, abs(float(g["pinn_gE"])))
+    loss, gWs, gbs, _ = O.rayleigh_loss(uW, ub, X, O.SIN, env, a=0.5, beta=V, eps_out=1e-12, scale=2 * L)
+    assert abs(loss - g["drm_loss"]) <= 1e-10 * max(1, abs(g["drm_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "drm_"), 1e-9, name + " drm")
+    # wan: pde = (2L m1 / (2L m2 + 1e-12))², norm = (2L m3 − 1)²; v-net is RAW FCN1D
+    u_net = dict(Ws=uW, bs=ub, act=O.SIN, env=env)
+    v_net = dict(Ws=vW, bs=vb, act=O.SIN, env=dict(kind=O.ENV_NONE))
+    m, Gu, Gv, dE1 = O.wan_means(u_net, v_net, X, None, -L, L, a=0.5, beta=V, E=E, eps_den=1e-10)
+    m1, m2, m3, _ = m
+    den = 2 * L * m2 + 1e-12
+    ratio = 2 * L * m1 / den
+    pde = ratio ** 2
+    nrm = (2 * L * m3 - 1.0) ** 2
+    assert abs(pde - g["wan_pde"]) <= 1e-9 * max(1, abs(g["wan_pde"]))
+    assert abs(nrm - g["wan_norm"]) <= 1e-9 * max(1, abs(g["wan_norm"]))
+    d = [2 * ratio * 2 * L / den, -2 * ratio * 2 * L * m1 * 2 * L / den ** 2, 2 * (2 * L * m3 - 1.0) * 2 * L, 0.0]
+    assert_grads_close(_combine(Gu, d), grads_from(g, "wan_u_"), 1e-8, "wan/u")
+    assert_grads_close(_combine(Gv, d), grads_from(g, "wan_v_"), 1e-8, "wan/v")
+    assert abs(d[0] * dE1 - float(g["wan_gE"])) <= 1e-8 * max(1, abs(float(g["wan_gE"])))
