@@ -1,0 +1,164 @@
+/* pde_b200.h — C ABI of the B200 collocation-point loss-step library (libpde_b200.so).
+ *
+ * The reference (JiakangC/Neural-Network-Based-PDE-Solver) has no FFI layer: its operator
+ * boundary for this path is the set of module-level Python loss functions, which obtain
+ * u, grad u, the Laplacian and the parameter gradients from nested torch.autograd calls.
+ * Each entry point below names the reference interface it replaces (paths are relative to
+ * the reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain C99 types; every pointer marked "device" is CUDA device memory owned by the caller;
+ *   - every call returns 0 on success or a negative pde_status; pde_strerror() names it;
+ *   - nothing is allocated by the library and no state is kept between calls; all work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation, so the
+ *     calls are CUDA-graph capturable;
+ *   - floating point type is per network (PDE_F32 / PDE_F64); all device arrays of one call
+ *     use that type; points X are (n, dim) row-major; jets J are (n, C) row-major with
+ *     C = 1 + order*dim channels: value, dim first derivatives, dim second-derivative diagonal;
+ *   - parameter gradients are written as ONE flat vector in nn.Module.parameters() order:
+ *     W_0 (out,in) row-major, b_0, W_1, b_1, ...
+ */
+#ifndef PDE_B200_H
+#define PDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDE_ABI_VERSION 1
+#define PDE_MAX_LINEAR 8   /* Linear layers per network */
+#define PDE_MAX_DIM 5      /* spatial dimension d = 1..5 (README.md:23 of the reference) */
+#define PDE_MAX_NODES 8    /* forced-node roots per dimension */
+#define PDE_MAX_Q 4        /* per-point quantities a program may average */
+#define PDE_MAX_WIDTH 256  /* hidden width */
+
+typedef enum {
+  PDE_OK = 0,
+  PDE_ERR_INVALID = -1,      /* null pointer / bad enum / bad size */
+  PDE_ERR_UNSUPPORTED = -2,  /* shape outside what the kernels implement */
+  PDE_ERR_WORKSPACE = -3,    /* workspace too small */
+  PDE_ERR_CUDA = -4,         /* a CUDA runtime call failed (launch, attribute) */
+  PDE_ERR_NO_DEVICE = -5     /* no sm_100 device: there is no CPU fallback */
+} pde_status;
+
+enum { PDE_F32 = 0, PDE_F64 = 1 };
+enum { PDE_ACT_SIN = 0, PDE_ACT_TANH = 1 };
+enum { PDE_ENV_NONE = 0, PDE_ENV_POLY = 1, PDE_ENV_EXPWIN = 2 };
+enum {
+  PDE_PROG_PINN = 1,     /* q0 = (alpha*Lap(u) + (beta-E)*u - f)^2                order 2 */
+  PDE_PROG_DRM = 2,      /* q0 = alpha*|grad u|^2 - f*u                            order 1 */
+  PDE_PROG_RAYLEIGH = 3, /* q0 = alpha*|grad u|^2 + beta*u^2 ; q1 = u^2            order 1 */
+  PDE_PROG_MSE = 4       /* q0 = (u - f)^2  (f NULL -> u^2)                        order 0 */
+};
+
+/* A fully connected network [dim, H, ..., H, 1] with sin or tanh activations.
+ * Replaces: SolutionNet / CriticNet (Poisson_Equations/Poisson_ND.py:11-46), FCN
+ * (Schrodinger_Equations/.../IPW_1D_WAN.py:62-81, QHO_2D.py:103-114), FCN1D (KH_1D.py:104-112).
+ * W[l] is nn.Linear.weight of layer l, (widths[l+1], widths[l]) row-major; b[l] its bias. */
+typedef struct pde_net {
+  int32_t dtype;                      /* PDE_F32 | PDE_F64 */
+  int32_t dim;                        /* 1..PDE_MAX_DIM */
+  int32_t n_linear;                   /* 2..PDE_MAX_LINEAR */
+  int32_t activation;                 /* PDE_ACT_* */
+  int32_t widths[PDE_MAX_LINEAR + 1]; /* widths[0]=dim, hidden widths equal, widths[n_linear]=1 */
+  const void* W[PDE_MAX_LINEAR];      /* device */
+  const void* b[PDE_MAX_LINEAR];      /* device */
+} pde_net;
+
+/* Separable hard-constraint envelope u = B(x) * net(x), B = prod_i b(x_i).
+ * PDE_ENV_POLY   b(t) = (t-lo)(hi-t)                      Poisson_ND.py:27-29, IPW_1D_WAN.py:77-80
+ * PDE_ENV_EXPWIN b(t) = (1-exp(-(t-lo)))(1-exp(t-hi))     QHO_2D.py:149-153, KH_1D.py:117-120
+ * nodes: b(t) additionally times prod_k (t - nodes[i][k])  IPW_1D_PINN_DRM.py:44-51, QHO_2D.py:155-168 */
+typedef struct pde_envelope {
+  int32_t kind;
+  int32_t n_nodes[PDE_MAX_DIM];
+  double lo, hi;
+  double nodes[PDE_MAX_DIM][PDE_MAX_NODES];
+} pde_envelope;
+
+/* Per-point residual program evaluated on the jets of u = B*net.
+ * f, beta: optional device arrays of n values; energy: optional device scalar (trainable E,
+ * KH_1D.py:218, QHO_2D_Energy.py:287-291), else energy_const. */
+typedef struct pde_program {
+  int32_t kind;        /* PDE_PROG_* */
+  int32_t reserved;
+  double alpha;
+  double beta_const;   /* used when beta == NULL */
+  double energy_const; /* used when energy == NULL */
+  const void* f;       /* device, (n) or NULL */
+  const void* beta;    /* device, (n) or NULL */
+  const void* energy;  /* device scalar or NULL */
+} pde_program;
+
+int pde_abi_version(void);
+const char* pde_strerror(int status);
+
+/* Number of parameters (length of the flat gradient vector). */
+int pde_param_count(const pde_net* net, int64_t* n_params);
+
+/* Jet channels for (dim, order) and number of averaged quantities of a program kind. */
+int pde_jet_channels(int32_t dim, int32_t order);
+int pde_program_quantities(int32_t kind);
+int pde_program_order(int32_t kind);
+
+/* Workspace bytes needed by any of the calls below for this network / order / n points. */
+int pde_workspace_bytes(const pde_net* net, int32_t order, int64_t n_points, size_t* bytes);
+
+/* Network jets (value, gradient, Hessian diagonal of net(X), no envelope).
+ * Replaces: model.net(X) + grad_scalar_field + laplacian (Poisson_ND.py:61-71),
+ * compute_derivatives (QHO_1D_PINN_DRM.py:155-160).  J: device (n, C). */
+int pde_jets_forward(const pde_net* net, int32_t order, const void* X, int64_t n_points,
+                     void* J, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Reverse sweep of pde_jets_forward: grad[k] = sum_p sum_c Jbar[p,c] dJ[p,c]/dtheta_k.
+ * Replaces: loss.backward() through the nested autograd graph (Poisson_ND.py:240).
+ * The forward is recomputed tile by tile on chip; nothing but X and Jbar is read. */
+int pde_jets_backward(const pde_net* net, int32_t order, const void* X, int64_t n_points,
+                      const void* Jbar, void* grad, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Fused loss step: forward jets, envelope, residual program, per-point seeds and the reverse
+ * sweep in one pass per tile of points.
+ * Replaces: pinn_residual_loss / drm_energy_loss (+ .backward()) (Poisson_ND.py:91-103,:240),
+ * PINN_loss / DRM_loss (IPW_1D_PINN_DRM.py:63-90), pinn_loss / drm_loss (KH_1D.py:226-242),
+ * the inline residual blocks (QHO_2D.py:363-383, IPW_2D.py:195-228), boundary / data / norm
+ * value terms (Poisson_ND.py:130-147,230-232).
+ *   sums   : device (K) out — sum_p q_k(p) (raw sums; the caller divides by its global N)
+ *   grad   : device (n_params) out or NULL — sum_k seed[k] * inv_n * sum_p dq_k(p)/dtheta
+ *   energy_grad : device scalar out or NULL — same contraction for dq/dE
+ *   seed   : device (K) or NULL (all ones) — dLoss/dmean_k, lets functions of means
+ *            (Rayleigh quotient, WAN) and multi-GPU exact recombination share one kernel. */
+int pde_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog,
+                           const void* X, int64_t n_points, const void* seed, double inv_n,
+                           void* sums, void* grad, void* energy_grad, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* WAN weak-form coupling of two networks on their jets (order 1), elementwise.
+ * Replaces: bump_w + wan_losses (Poisson_ND.py:74-88,105-128), function_w + WAN_loss
+ * (IPW_1D_WAN.py:31-59,88-115; QHO_2D.py:172-225), weight_fn_w + wan_loss (KH_1D.py:138-148,244-269).
+ *   q0 = alpha*grad u . grad phi + (beta-E)*u*phi - f*phi, q1 = phi^2, q2 = u^2, q3 = |grad v|^2 + v^2,
+ *   phi = w*v, w = prod_i bump((x_i-c)/h) on [w_lo, w_hi], bump(t) = exp(1/(t^2-1+eps_den))/0.210987.
+ *   Ju, Jv  : device (n, 1+dim) network jets of u-net / v-net (pde_jets_forward, order 1)
+ *   sums    : device (5) out — sum_p q0..q3 and sum_p dq0/dE
+ *   seed    : device (4) or NULL; when Jbar_u / Jbar_v are non-NULL they receive
+ *             sum_k seed[k]*inv_n*dq_k/dJ (cotangents for pde_jets_backward). */
+typedef struct pde_wan {
+  int32_t dtype, dim;
+  double alpha, beta_const, energy_const, w_lo, w_hi, eps_den;
+  const void* f;      /* device (n) or NULL */
+  const void* beta;   /* device (n) or NULL */
+  const void* energy; /* device scalar or NULL */
+  pde_envelope env_u, env_v;
+} pde_wan;
+
+int pde_wan_pointwise(const pde_wan* wan, const void* X, int64_t n_points, const void* Ju,
+                      const void* Jv, const void* seed, double inv_n, void* sums, void* Jbar_u,
+                      void* Jbar_v, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDE_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of libpde_b200.so (include/pde_b200.h).
+
+The library is the product; there is no Python or CPU fallback.  ``load()`` raises if the
+shared object has not been built (``python __graft_entry__.py build`` or ``make -C csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_LINEAR, MAX_DIM, MAX_NODES, MAX_Q = 8, 5, 8, 4
+F32, F64 = 0, 1
+ACT_SIN, ACT_TANH = 0, 1
+ENV_NONE, ENV_POLY, ENV_EXPWIN = 0, 1, 2
+PROG_PINN, PROG_DRM, PROG_RAYLEIGH, PROG_MSE = 1, 2, 3, 4
+
+EXPORTS = [
+    "pde_abi_version", "pde_strerror", "pde_param_count", "pde_jet_channels", "pde_program_quantities",
+    "pde_program_order", "pde_workspace_bytes", "pde_jets_forward", "pde_jets_backward",
+    "pde_residual_loss_grad", "pde_wan_pointwise",
+]
+
+
+class Net(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("dim", C.c_int32), ("n_linear", C.c_int32), ("activation", C.c_int32),
+                ("widths", C.c_int32 * (MAX_LINEAR + 1)), ("W", C.c_void_p * MAX_LINEAR), ("b", C.c_void_p * MAX_LINEAR)]
+
+
+class Envelope(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_nodes", C.c_int32 * MAX_DIM), ("lo", C.c_double), ("hi", C.c_double),
+                ("nodes", (C.c_double * MAX_NODES) * MAX_DIM)]
+
+
+class Program(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("alpha", C.c_double), ("beta_const", C.c_double),
+                ("energy_const", C.c_double), ("f", C.c_void_p), ("beta", C.c_void_p), ("energy", C.c_void_p)]
+
+
+class Wan(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("dim", C.c_int32), ("alpha", C.c_double), ("beta_const", C.c_double),
+                ("energy_const", C.c_double), ("w_lo", C.c_double), ("w_hi", C.c_double), ("eps_den", C.c_double),
+                ("f", C.c_void_p), ("beta", C.c_void_p), ("energy", C.c_void_p),
+                ("env_u", Envelope), ("env_v", Envelope)]
+
+
+class PdeError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpde_b200.so")
+
+
+def load():
+    """Load the CUDA library; fail loudly when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PdeError(f"{path} not built: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                       "There is no CPU fallback for the collocation kernels.")
+    lib = C.CDLL(path)
+    vp, sz, i32, i64, dbl = C.c_void_p, C.c_size_t, C.c_int32, C.c_int64, C.c_double
+    lib.pde_abi_version.restype = C.c_int
+    lib.pde_strerror.restype = C.c_char_p
+    lib.pde_strerror.argtypes = [C.c_int]
+    lib.pde_param_count.argtypes = [C.POINTER(Net), C.POINTER(i64)]
+    lib.pde_jet_channels.argtypes = [i32, i32]
+    lib.pde_program_quantities.argtypes = [i32]
+    lib.pde_program_order.argtypes = [i32]
+    lib.pde_workspace_bytes.argtypes = [C.POINTER(Net), i32, i64, C.POINTER(sz)]
+    lib.pde_jets_forward.argtypes = [C.POINTER(Net), i32, vp, i64, vp, vp, sz, vp]
+    lib.pde_jets_backward.argtypes = [C.POINTER(Net), i32, vp, i64, vp, vp, vp, sz, vp]
+    lib.pde_residual_loss_grad.argtypes = [C.POINTER(Net), C.POINTER(Envelope), C.POINTER(Program), vp, i64, vp, dbl,
+                                           vp, vp, vp, vp, sz, vp]
+    lib.pde_wan_pointwise.argtypes = [C.POINTER(Wan), vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, sz, vp]
+    for name in EXPORTS:
+        if name not in ("pde_strerror",):
+            getattr(lib, name).restype = C.c_int
+    if lib.pde_abi_version() != 1:
+        raise PdeError("libpde_b200.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().pde_strerror(status).decode()
+        if status == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        if status == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise PdeError(f"{what}: {msg} (status {status})")

@@ -1,0 +1,476 @@
+"""torch.autograd bridge over the C ABI (include/pde_b200.h).
+
+Three operators, all running on hand-written CUDA kernels:
+
+* ``mlp_jets(model, X, order)``      network value / gradient / Hessian-diagonal channels, with a
+                                      reverse sweep into the parameters (replaces ``model.net(X)`` +
+                                      nested ``autograd.grad`` — Poisson_ND.py:61-71).
+* ``residual_means(...)``            fused forward + envelope + residual program + reverse sweep
+                                      (replaces pinn_residual_loss / drm_energy_loss + backward,
+                                      Poisson_ND.py:91-103,:240 and the Schrödinger equivalents).
+* ``wan_means(...)``                 two-network WAN coupling on the jets (Poisson_ND.py:105-128).
+
+Every operator returns *means* ``m_k``; the scalar loss ``F(m_1..m_K)`` stays in Python on 0-d
+tensors.  With ``group`` given, the sums (and gradient vectors) are all-reduced so that the result
+equals the single big batch exactly, also for functions of means.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+# ---------------------------------------------------------------------------------------------
+# network / envelope descriptions
+# ---------------------------------------------------------------------------------------------
+
+
+def _linear_stack(model: nn.Module):
+    """(linears, activation) of a reference-style network.
+
+    Accepts the reference's own modules: an ``nn.Sequential`` under ``.net`` with Linear at even
+    indices (Poisson_ND.py:17-23, IPW_1D_WAN.py:67-73, KH_1D.py:108-112), ``UnifiedEigenModel``
+    (``.u_model.net``, KH_1D.py:216-217), a ``ModuleList`` under ``.layers``
+    (QHO_1D_PINN_DRM.py:64-66) or a bare Sequential.
+    """
+    seq = model
+    if hasattr(model, "u_model"):
+        seq = model.u_model
+    if hasattr(seq, "net"):
+        seq = seq.net
+    elif hasattr(seq, "layers"):
+        seq = seq.layers
+    mods = list(seq)
+    linears = [m for m in mods if isinstance(m, nn.Linear)]
+    others = [m for m in mods if not isinstance(m, nn.Linear)]
+    if not linears:
+        raise ValueError("model has no nn.Linear layers")
+    act = None
+    for m in others:
+        name = type(m).__name__.lower()
+        a = "tanh" if "tanh" in name else ("sin" if name.startswith("sin") else None)
+        if a is None:
+            raise NotImplementedError(f"activation {type(m).__name__} is not supported (sin / tanh only)")
+        if act is not None and a != act:
+            raise NotImplementedError("mixed activations are not supported")
+        act = a
+    if act is None:  # ModuleList of Linear only: activation kept as an attribute
+        a = getattr(model, "activation", None)
+        name = (type(a).__name__ if a is not None else "sin").lower()
+        act = "tanh" if "tanh" in name else "sin"
+    return linears, act
+
+
+@dataclass
+class EnvelopeSpec:
+    """Separable hard-constraint factor (pde_envelope)."""
+    kind: int = L.ENV_NONE
+    lo: float = 0.0
+    hi: float = 0.0
+    nodes: Sequence[Sequence[float]] = field(default_factory=list)
+
+    def to_c(self) -> L.Envelope:
+        e = L.Envelope()
+        e.kind, e.lo, e.hi = int(self.kind), float(self.lo), float(self.hi)
+        for i, ns in enumerate(self.nodes):
+            if len(ns) > L.MAX_NODES:
+                raise NotImplementedError("too many forced nodes")
+            e.n_nodes[i] = len(ns)
+            for k, v in enumerate(ns):
+                e.nodes[i][k] = float(v)
+        return e
+
+
+NO_ENVELOPE = EnvelopeSpec()
+
+
+class _Net:
+    """Device-side view of a model's parameters for one call."""
+
+    def __init__(self, model: nn.Module, X: torch.Tensor):
+        self.linears, act = _linear_stack(model)
+        if not X.is_cuda:
+            raise L.PdeError("collocation kernels run on CUDA tensors only (no CPU fallback)")
+        if X.dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError("float32 / float64 only")
+        self.dtype = X.dtype
+        self.params = []
+        for m in self.linears:
+            if m.bias is None:
+                raise NotImplementedError("Linear layers without bias are not supported")
+            self.params += [m.weight, m.bias]
+        for p in self.params:
+            if p.device != X.device or p.dtype != X.dtype:
+                raise ValueError("model parameters and points must share device and dtype")
+        self.act = L.ACT_TANH if act == "tanh" else L.ACT_SIN
+        self.widths = [self.linears[0].in_features] + [m.out_features for m in self.linears]
+        self.dim = self.widths[0]
+
+    def to_c(self, tensors) -> L.Net:
+        n = L.Net()
+        n.dtype = L.F64 if self.dtype == torch.float64 else L.F32
+        n.dim, n.n_linear, n.activation = self.dim, len(self.linears), self.act
+        if len(self.linears) > L.MAX_LINEAR:
+            raise NotImplementedError("too many layers")
+        for i, w in enumerate(self.widths):
+            n.widths[i] = w
+        for l in range(len(self.linears)):
+            n.W[l] = tensors[2 * l].data_ptr()
+            n.b[l] = tensors[2 * l + 1].data_ptr()
+        return n
+
+
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def _ws_for(cnet, order, n, device):
+    need = C.c_size_t(0)
+    L.check(L.load().pde_workspace_bytes(C.byref(cnet), order, n, C.byref(need)), "pde_workspace_bytes")
+    return _workspace(device, need.value)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _split_flat(flat, params):
+    out, o = [], 0
+    for p in params:
+        k = p.numel()
+        out.append(flat[o:o + k].view_as(p))
+        o += k
+    return out
+
+
+def _points(X):
+    if X.dim() == 1:
+        X = X.view(-1, 1)
+    if X.dim() != 2:
+        raise ValueError("points must be (N, d)")
+    return X.detach().contiguous()
+
+
+def _all_reduce(t, group):
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+# ---------------------------------------------------------------------------------------------
+# network jets
+# ---------------------------------------------------------------------------------------------
+class _Jets(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net: _Net, order: int, X: torch.Tensor, *params):
+        lib = L.load()
+        ps = [p.detach().contiguous() for p in params]
+        cnet = net.to_c(ps)
+        n = X.shape[0]
+        Cc = 1 + order * net.dim
+        J = torch.empty(n, Cc, dtype=X.dtype, device=X.device)
+        ws = _ws_for(cnet, order, n, X.device)
+        with torch.cuda.device(X.device):
+            L.check(lib.pde_jets_forward(C.byref(cnet), order, X.data_ptr(), n, J.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _stream(X.device)), "pde_jets_forward")
+        ctx.net, ctx.order = net, order
+        ctx.save_for_backward(X, *ps)
+        return J
+
+    @staticmethod
+    def backward(ctx, Jbar):
+        lib = L.load()
+        X, *ps = ctx.saved_tensors
+        net, order = ctx.net, ctx.order
+        cnet = net.to_c(ps)
+        n = X.shape[0]
+        nparam = sum(p.numel() for p in ps)
+        grad = torch.empty(nparam, dtype=X.dtype, device=X.device)
+        Jb = Jbar.contiguous()
+        ws = _ws_for(cnet, order, n, X.device)
+        with torch.cuda.device(X.device):
+            L.check(lib.pde_jets_backward(C.byref(cnet), order, X.data_ptr(), n, Jb.data_ptr(), grad.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), _stream(X.device)), "pde_jets_backward")
+        grads = _split_flat(grad, ps)
+        need = ctx.needs_input_grad[3:]
+        return (None, None, None) + tuple(g if nd else None for g, nd in zip(grads, need))
+
+
+def mlp_jets(model: nn.Module, X: torch.Tensor, order: int = 2) -> torch.Tensor:
+    """(N, 1+order*d) jets of ``model.net`` at X (no envelope), differentiable w.r.t. the parameters."""
+    X = _points(X)
+    net = _Net(model, X)
+    return _Jets.apply(net, int(order), X, *net.params)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused residual programs
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ProgramSpec:
+    kind: int
+    alpha: float = 1.0
+    beta_const: float = 0.0
+    energy_const: float = 0.0
+
+
+class _Residual(torch.autograd.Function):
+    """means[K] of a residual program; backward = sum_k gbar_k * d(mean_k)/d(theta, E)."""
+
+    @staticmethod
+    def forward(ctx, net, env, spec, group, n_global, need_grad, X, f, beta, energy, *params):
+        lib = L.load()
+        ps = [p.detach().contiguous() for p in params]
+        cnet = net.to_c(ps)
+        n = X.shape[0]
+        K = lib.pde_program_quantities(spec.kind)
+        order = lib.pde_program_order(spec.kind)
+        dev, dt = X.device, X.dtype
+        nparam = sum(p.numel() for p in ps)
+        n_tot = float(n if n_global is None else n_global)
+        ctx.cfg = (net, env, spec, group, n_tot)
+        ctx.K = K
+        fused = (K == 1) and need_grad
+        # one buffer [grad (nparam) | dE (1) | sums (K)] so that one all-reduce covers everything
+        buf = torch.zeros(nparam + 1 + K, dtype=dt, device=dev)
+        prog = L.Program()
+        prog.kind, prog.alpha, prog.beta_const, prog.energy_const = spec.kind, spec.alpha, spec.beta_const, spec.energy_const
+        prog.f = f.data_ptr() if f is not None else None
+        prog.beta = beta.data_ptr() if beta is not None else None
+        e_dev = energy.detach().reshape(1).to(dt) if energy is not None else None
+        prog.energy = e_dev.data_ptr() if e_dev is not None else None
+        cenv = env.to_c()
+        ws = _ws_for(cnet, order, n, dev)
+        gptr = buf.data_ptr() if fused else None
+        eptr = buf.data_ptr() + nparam * buf.element_size() if fused else None
+        sptr = buf.data_ptr() + (nparam + 1) * buf.element_size()
+        with torch.cuda.device(dev):
+            L.check(lib.pde_residual_loss_grad(C.byref(cnet), C.byref(cenv), C.byref(prog), X.data_ptr(), n, None,
+                                               1.0 / n_tot, sptr, gptr, eptr, ws.data_ptr(), ws.numel(), _stream(dev)),
+                    "pde_residual_loss_grad")
+        if group is not None:
+            _all_reduce(buf if fused else buf[nparam + 1:], group)
+        means = buf[nparam + 1:] / n_tot
+        ctx.fused = fused
+        ctx.has_energy = energy is not None
+        if fused:
+            ctx.save_for_backward(buf)
+            ctx.shapes = [p.shape for p in ps]
+        else:
+            ctx.save_for_backward(X, f, beta, e_dev, *ps)
+        return means.clone()
+
+    @staticmethod
+    def backward(ctx, gmeans):
+        net, env, spec, group, n_tot = ctx.cfg
+        n_in = 10
+        if ctx.fused:
+            (buf,) = ctx.saved_tensors
+            nparam = buf.numel() - 1 - ctx.K
+            flat = buf[:nparam] * gmeans[0]
+            gE = (buf[nparam] * gmeans[0]) if ctx.has_energy else None
+            grads, o = [], 0
+            for shp in ctx.shapes:
+                k = 1
+                for s in shp:
+                    k *= s
+                grads.append(flat[o:o + k].view(shp)); o += k
+        else:
+            lib = L.load()
+            X, f, beta, e_dev, *ps = ctx.saved_tensors
+            cnet = net.to_c(ps)
+            n = X.shape[0]
+            dev, dt = X.device, X.dtype
+            nparam = sum(p.numel() for p in ps)
+            buf = torch.zeros(nparam + 1 + ctx.K, dtype=dt, device=dev)
+            prog = L.Program()
+            prog.kind, prog.alpha, prog.beta_const, prog.energy_const = spec.kind, spec.alpha, spec.beta_const, spec.energy_const
+            prog.f = f.data_ptr() if f is not None else None
+            prog.beta = beta.data_ptr() if beta is not None else None
+            prog.energy = e_dev.data_ptr() if e_dev is not None else None
+            cenv = env.to_c()
+            order = lib.pde_program_order(spec.kind)
+            seed = gmeans.detach().to(dt).contiguous()
+            ws = _ws_for(cnet, order, n, dev)
+            with torch.cuda.device(dev):
+                L.check(lib.pde_residual_loss_grad(C.byref(cnet), C.byref(cenv), C.byref(prog), X.data_ptr(), n,
+                                                   seed.data_ptr(), 1.0 / n_tot,
+                                                   buf.data_ptr() + (nparam + 1) * buf.element_size(), buf.data_ptr(),
+                                                   buf.data_ptr() + nparam * buf.element_size(), ws.data_ptr(),
+                                                   ws.numel(), _stream(dev)), "pde_residual_loss_grad")
+            if group is not None:
+                _all_reduce(buf[:nparam + 1], group)
+            grads = _split_flat(buf[:nparam], ps)
+            gE = buf[nparam] if ctx.has_energy else None
+        need = ctx.needs_input_grad
+        out = [None] * n_in
+        if gE is not None and need[9]:
+            out[9] = gE.reshape(())
+        out += [g if nd else None for g, nd in zip(grads, need[n_in:])]
+        return tuple(out)
+
+
+def residual_means(model, X, spec: ProgramSpec, env: EnvelopeSpec = NO_ENVELOPE, f=None, beta=None, energy=None,
+                   group=None, n_global: Optional[int] = None) -> torch.Tensor:
+    """Means of the program's per-point quantities, differentiable w.r.t. the network parameters
+    (and the scalar ``energy`` when it is a tensor that requires grad)."""
+    X = _points(X)
+    net = _Net(model, X)
+    n = X.shape[0]
+
+    def coef(t):
+        if t is None:
+            return None
+        t = t.detach().to(X.dtype).reshape(-1).contiguous()
+        if t.numel() != n or t.device != X.device:
+            raise ValueError("per-point coefficient must have one value per point on the points' device")
+        return t
+
+    e = None
+    if energy is not None:
+        if torch.is_tensor(energy):
+            e = energy
+        else:
+            spec = ProgramSpec(spec.kind, spec.alpha, spec.beta_const, float(energy))
+    if beta is not None and not torch.is_tensor(beta):
+        spec = ProgramSpec(spec.kind, spec.alpha, float(beta), spec.energy_const)
+        beta = None
+    # (grad mode is off inside Function.forward, so decide here whether the fused reverse sweep runs)
+    need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in net.params) or
+                                             (e is not None and e.requires_grad))
+    return _Residual.apply(net, env, spec, group, n_global, need_grad, X, coef(f), coef(beta), e, *net.params)
+
+
+# ---------------------------------------------------------------------------------------------
+# WAN coupling of two networks
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class WanSpec:
+    alpha: float = 1.0
+    beta_const: float = 0.0
+    energy_const: float = 0.0
+    w_lo: float = 0.0
+    w_hi: float = 2.0
+    eps_den: float = 0.0
+
+
+class _WanPoint(torch.autograd.Function):
+    """means[4] (+ d mean0/dE) from the two networks' jets; backward produces jet cotangents."""
+
+    @staticmethod
+    def forward(ctx, spec, env_u, env_v, group, n_global, X, f, beta, energy, Ju, Jv):
+        lib = L.load()
+        n, d = X.shape
+        dev, dt = X.device, X.dtype
+        n_tot = float(n if n_global is None else n_global)
+        w = L.Wan()
+        w.dtype = L.F64 if dt == torch.float64 else L.F32
+        w.dim = d
+        w.alpha, w.beta_const, w.energy_const = spec.alpha, spec.beta_const, spec.energy_const
+        w.w_lo, w.w_hi, w.eps_den = spec.w_lo, spec.w_hi, spec.eps_den
+        w.f = f.data_ptr() if f is not None else None
+        w.beta = beta.data_ptr() if beta is not None else None
+        e_dev = energy.detach().reshape(1).to(dt) if energy is not None else None
+        w.energy = e_dev.data_ptr() if e_dev is not None else None
+        w.env_u, w.env_v = env_u.to_c(), env_v.to_c()
+        sums = torch.zeros(5, dtype=dt, device=dev)
+        ws = _workspace(dev, 1 << 20)
+        Juc, Jvc = Ju.detach().contiguous(), Jv.detach().contiguous()
+        with torch.cuda.device(dev):
+            L.check(lib.pde_wan_pointwise(C.byref(w), X.data_ptr(), n, Juc.data_ptr(), Jvc.data_ptr(), None, 1.0 / n_tot,
+                                          sums.data_ptr(), None, None, ws.data_ptr(), ws.numel(), _stream(dev)),
+                    "pde_wan_pointwise")
+        if group is not None:
+            _all_reduce(sums, group)
+        ctx.cfg = (spec, env_u, env_v, n_tot)
+        ctx.has_energy = energy is not None
+        ctx.save_for_backward(X, f, beta, e_dev, Juc, Jvc, sums)
+        return sums[:4] / n_tot
+
+    @staticmethod
+    def backward(ctx, gmeans):
+        lib = L.load()
+        spec, env_u, env_v, n_tot = ctx.cfg
+        X, f, beta, e_dev, Ju, Jv, sums = ctx.saved_tensors
+        n, d = X.shape
+        dev, dt = X.device, X.dtype
+        w = L.Wan()
+        w.dtype = L.F64 if dt == torch.float64 else L.F32
+        w.dim = d
+        w.alpha, w.beta_const, w.energy_const = spec.alpha, spec.beta_const, spec.energy_const
+        w.w_lo, w.w_hi, w.eps_den = spec.w_lo, spec.w_hi, spec.eps_den
+        w.f = f.data_ptr() if f is not None else None
+        w.beta = beta.data_ptr() if beta is not None else None
+        w.energy = e_dev.data_ptr() if e_dev is not None else None
+        w.env_u, w.env_v = env_u.to_c(), env_v.to_c()
+        seed = gmeans.detach().to(dt).contiguous()
+        Jbu, Jbv = torch.empty_like(Ju), torch.empty_like(Jv)
+        scratch = torch.empty(5, dtype=dt, device=dev)
+        ws = _workspace(dev, 1 << 20)
+        with torch.cuda.device(dev):
+            L.check(lib.pde_wan_pointwise(C.byref(w), X.data_ptr(), n, Ju.data_ptr(), Jv.data_ptr(), seed.data_ptr(),
+                                          1.0 / n_tot, scratch.data_ptr(), Jbu.data_ptr(), Jbv.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), _stream(dev)), "pde_wan_pointwise")
+        gE = None
+        if ctx.has_energy and ctx.needs_input_grad[8]:
+            gE = (sums[4] / n_tot * gmeans[0]).reshape(())   # sums already all-reduced in forward
+        need = ctx.needs_input_grad
+        return (None, None, None, None, None, None, None, None, gE, Jbu if need[9] else None, Jbv if need[10] else None)
+
+
+def wan_means(u_model, v_model, X, spec: WanSpec, env_u=NO_ENVELOPE, env_v=NO_ENVELOPE, f=None, beta=None, energy=None,
+              group=None, n_global=None):
+    """means (q0..q3) of the WAN weak-form quantities for the u / v networks (pde_wan_pointwise).
+
+    The jets of both networks come from the fused network kernels; parameters with
+    ``requires_grad=False`` (the reference toggles them, IPW_1D_WAN.py:186-200) get no gradient.
+    With ``group`` the per-rank parameter gradients are averaged exactly because the means are
+    all-reduced before ``F`` is applied and the cotangents carry 1/N_global.
+    """
+    X = _points(X)
+    n = X.shape[0]
+
+    def coef(t):
+        if t is None:
+            return None
+        return t.detach().to(X.dtype).reshape(-1).contiguous()
+
+    e = None
+    if energy is not None:
+        if torch.is_tensor(energy):
+            e = energy
+        else:
+            spec = WanSpec(spec.alpha, spec.beta_const, float(energy), spec.w_lo, spec.w_hi, spec.eps_den)
+    if beta is not None and not torch.is_tensor(beta):
+        spec = WanSpec(spec.alpha, float(beta), spec.energy_const, spec.w_lo, spec.w_hi, spec.eps_den)
+        beta = None
+    Ju = mlp_jets(u_model, X, 1)
+    Jv = mlp_jets(v_model, X, 1)
+    means = _WanPoint.apply(spec, env_u, env_v, group, n_global, X, coef(f), coef(beta), e, Ju, Jv)
+    return means
+
+
+def all_reduce_grads(params, group=None):
+    """Sum ``p.grad`` over ranks (used with wan_means, whose network sweeps are rank local)."""
+    import torch.distributed as dist
+    gs = [p.grad for p in params if p.grad is not None]
+    if not gs:
+        return
+    flat = torch.cat([g.reshape(-1) for g in gs])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for g in gs:
+        k = g.numel()
+        g.copy_(flat[o:o + k].view_as(g)); o += k
