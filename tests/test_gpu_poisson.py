@@ -28,6 +28,7 @@ def _model_from(pb, g, bc, dtype, prefix="", cls=None):
     Ws, bs = net_from(g, prefix)
     d, w, depth = Ws[0].shape[1], Ws[0].shape[0], len(Ws)
     m = (cls or pb.poisson.SolutionNet)(d, w, depth, bc) if cls is None else cls(d, w, depth)
+    m = m.double()
     lin = [x for x in m.net if isinstance(x, torch.nn.Linear)]
     with torch.no_grad():
         for l, W, b in zip(lin, Ws, bs):
@@ -92,7 +93,7 @@ def test_jets_backward_matches_oracle(dtype):
         for i in range(depth - 1):
             mods += [torch.nn.Linear(Ws[i].shape[1], w), pb.poisson.Sin() if act == "sin" else torch.nn.Tanh()]
         mods += [torch.nn.Linear(w, 1)]
-        net = torch.nn.Sequential(*mods)
+        net = torch.nn.Sequential(*mods).double()
         lin = [x for x in net if isinstance(x, torch.nn.Linear)]
         with torch.no_grad():
             for l, W, b in zip(lin, Ws, bs):
