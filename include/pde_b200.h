@@ -136,6 +136,10 @@ int pde_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pd
                            void* sums, void* grad, void* energy_grad, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* Which kernel family pde_residual_loss_grad uses for this network / program / size:
+ * 0 = generic SIMT FMA kernel, 1 = tcgen05 tensor-core kernel; negative = pde_status. Pure query. */
+int pde_query_path(const pde_net* net, const pde_program* prog, int64_t n_points);
+
 /* WAN weak-form coupling of two networks on their jets (order 1), elementwise.
  * Replaces: bump_w + wan_losses (Poisson_ND.py:74-88,105-128), function_w + WAN_loss
  * (IPW_1D_WAN.py:31-59,88-115; QHO_2D.py:172-225), weight_fn_w + wan_loss (KH_1D.py:138-148,244-269).

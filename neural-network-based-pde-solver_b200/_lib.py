@@ -17,7 +17,7 @@ PROG_PINN, PROG_DRM, PROG_RAYLEIGH, PROG_MSE = 1, 2, 3, 4
 EXPORTS = [
     "pde_abi_version", "pde_strerror", "pde_param_count", "pde_jet_channels", "pde_program_quantities",
     "pde_program_order", "pde_workspace_bytes", "pde_jets_forward", "pde_jets_backward",
-    "pde_residual_loss_grad", "pde_wan_pointwise",
+    "pde_residual_loss_grad", "pde_wan_pointwise", "pde_query_path",
 ]
 
 
@@ -77,6 +77,7 @@ def load():
     lib.pde_jets_backward.argtypes = [C.POINTER(Net), i32, vp, i64, vp, vp, vp, sz, vp]
     lib.pde_residual_loss_grad.argtypes = [C.POINTER(Net), C.POINTER(Envelope), C.POINTER(Program), vp, i64, vp, dbl,
                                            vp, vp, vp, vp, sz, vp]
+    lib.pde_query_path.argtypes = [C.POINTER(Net), C.POINTER(Program), i64]
     lib.pde_wan_pointwise.argtypes = [C.POINTER(Wan), vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, sz, vp]
     for name in EXPORTS:
         if name not in ("pde_strerror",):

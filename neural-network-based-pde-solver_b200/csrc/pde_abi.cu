@@ -348,6 +348,13 @@ int pde_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pd
                         energy_grad, workspace, workspace_bytes, st);
 }
 
+int pde_query_path(const pde_net* net, const pde_program* prog, int64_t n_points) {
+  int st = validate_net(net);
+  if (st) return st;
+  if (!prog) return PDE_ERR_INVALID;
+  return pde::tc_supported(net, prog, n_points) ? 1 : 0;
+}
+
 int pde_wan_pointwise(const pde_wan* wan, const void* X, int64_t n_points, const void* Ju, const void* Jv,
                       const void* seed, double inv_n, void* sums, void* Jbar_u, void* Jbar_v, void* workspace,
                       size_t workspace_bytes, void* stream) {

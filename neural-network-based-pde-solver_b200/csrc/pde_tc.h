@@ -7,6 +7,7 @@
 #include "../../include/pde_b200.h"
 
 namespace pde {
+bool tc_supported(const pde_net* net, const pde_program* prog, long long n_points);
 int tc_workspace_bytes(const pde_net* net, int order, long long n_points, size_t* bytes);
 int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
                           long long n_points, const void* seed, double inv_n, void* sums, void* grad,

@@ -127,6 +127,32 @@ class _Net:
 
 _WS = {}
 
+# bench.py sets this to a list to collect (start, stop) CUDA events around each fused-kernel ABI call
+KERNEL_EVENTS = None
+_LAST_PATH = "none"
+
+
+def last_kernel_path():
+    """Which kernel family served the last fused residual call ("simt_fma" or "tcgen05")."""
+    return _LAST_PATH
+
+
+class _timed:
+    def __init__(self, dev):
+        self.on = KERNEL_EVENTS is not None
+        if self.on:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.dev = dev
+
+    def __enter__(self):
+        if self.on:
+            self.a.record(torch.cuda.current_stream(self.dev))
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.b.record(torch.cuda.current_stream(self.dev))
+            KERNEL_EVENTS.append((self.a, self.b))
+
 
 def _workspace(device, nbytes):
     key = (device, torch.cuda.current_stream(device).cuda_stream)
@@ -256,10 +282,12 @@ class _Residual(torch.autograd.Function):
         gptr = buf.data_ptr() if fused else None
         eptr = buf.data_ptr() + nparam * buf.element_size() if fused else None
         sptr = buf.data_ptr() + (nparam + 1) * buf.element_size()
-        with torch.cuda.device(dev):
+        global _LAST_PATH
+        with torch.cuda.device(dev), _timed(dev):
             L.check(lib.pde_residual_loss_grad(C.byref(cnet), C.byref(cenv), C.byref(prog), X.data_ptr(), n, None,
                                                1.0 / n_tot, sptr, gptr, eptr, ws.data_ptr(), ws.numel(), _stream(dev)),
                     "pde_residual_loss_grad")
+        _LAST_PATH = "tcgen05" if lib.pde_query_path(C.byref(cnet), C.byref(prog), n) == 1 else "simt_fma"
         if group is not None:
             _all_reduce(buf if fused else buf[nparam + 1:], group)
         means = buf[nparam + 1:] / n_tot
