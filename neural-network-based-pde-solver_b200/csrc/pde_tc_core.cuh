@@ -1,0 +1,159 @@
+// pde_tc_core.cuh — tcgen05 / TMEM / mbarrier primitives and the shared-memory operand layout of
+// the tensor-core collocation kernel (sm_100a inline PTX, no CUTLASS).
+//
+// Operand tile ("Tile64"): 64 rows x 64 bf16 (128 B per row) stored as 8-row, 1024-byte
+// SWIZZLE_128B atoms: 16-byte chunk c of row r lives at
+//     (r/8)*1024 + (r%8)*128 + ((c ^ (r%8)) * 16).
+// The same bytes are simultaneously
+//   * a K-major  UMMA operand whose M/N index is the row and whose K index runs along the row, and
+//   * an MN-major UMMA operand whose K index is the row and whose M/N index runs along the row,
+// because both canonical layouts apply Swizzle<3,4,3> to the same address bits.  This is what
+// lets one copy of W serve the forward (B = W, K-major) and dgrad (B = W^T, MN-major), and one
+// copy of an activation / adjoint tile serve as A of the forward / dgrad GEMM (K-major) and as an
+// operand of the wgrad GEMM (MN-major, contraction over points).
+//
+// Accumulators use UMMA M = 64: row r of D lives in TMEM lane (r % 16) + 32 * (r / 16), so each
+// warp quarter holds 16 rows in its lanes 0..15; a second accumulator can be interleaved at lane
+// offset 16.  The epilogue reads them with tcgen05.ld.16x256b, whose register fragment is
+//   thread T:  {row T/4, cols 2(T%4), 2(T%4)+1}, {row T/4 + 8, same cols}      (+8 cols per repeat)
+// i.e. all 32 threads of a warp are busy on a 16-row x 8-column block.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pde {
+namespace tc {
+
+constexpr int TILE_BYTES = 8192;  // 64 rows x 128 B
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// byte offset of 16-byte chunk c (0..7) of row r inside a Tile64
+__host__ __device__ __forceinline__ uint32_t tile_off(int r, int c) {
+  return ((r >> 3) << 10) + ((r & 7) << 7) + (((c ^ (r & 7)) & 7) << 4);
+}
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- tcgen05
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// whole warp; writes the TMEM base address to *smem_dst
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, Blackwell descriptor version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// K-major view of a Tile64, K-step ks (16 elements = 32 B along the row)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_saddr, int ks) {
+  return make_desc(tile_saddr + ks * 32, 16, 1024);
+}
+// MN-major view of a Tile64, K-step ks (16 rows = two 8-row atoms = 2048 B)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, int ks) {
+  return make_desc(tile_saddr + ks * 2048, 8192, 1024);
+}
+
+// instruction descriptor for kind::f16, bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// TMEM address = base + (lane << 16) + column
+__device__ __forceinline__ uint32_t taddr_of(uint32_t base, int lane, int col) {
+  return base + (static_cast<uint32_t>(lane) << 16) + static_cast<uint32_t>(col);
+}
+
+// 16 lanes x 8 columns: v[0],v[1] = row T/4, cols 2(T%4)+{0,1};  v[2],v[3] = row T/4+8, same cols
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, float (&v)[4]) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(taddr));
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- bf16 hi/lo split of fp32 values:  x ~= hi + lo, each bf16 (round to nearest)
+// packs (a -> low half, b -> high half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+  lo = pack_bf16x2(a - ha, b - hb);
+}
+
+}  // namespace tc
+}  // namespace pde
