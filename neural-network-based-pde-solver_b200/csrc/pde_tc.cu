@@ -1,10 +1,984 @@
-// pde_tc.cu — tcgen05 path (placeholder until the tensor-core kernel lands: declines every shape).
+// pde_tc.cu — Blackwell tensor-core (tcgen05 / TMEM) fused collocation loss step, fp32 parity
+// through 3-term bf16 operand splits (x = hi + lo; hi*hi + lo*hi + hi*lo, fp32 accumulate).
+//
+// What it computes is the reference's nested-autograd step (Poisson_Equations/Poisson_ND.py:61-71
+// grad / Laplacian, :91-103 PINN / Deep-Ritz losses, :240 loss.backward()) for networks
+// [d, H<=64, ..., H, 1] with 2..4 hidden layers, restated as
+//   * forward-mode jets with a *Laplacian* channel instead of d second-derivative channels:
+//       channels (value, d_1..d_d, Lap):  z = W a (+b on the value channel),
+//       a0 = s(z0),  a_i = s'(z0) z_i,  aL = s'(z0) zL + s''(z0) sum_i z_i^2,
+//     which is the same quantity the reference sums from the Hessian diagonal (Poisson_ND.py:67-71);
+//   * the reverse sweep of that recurrence, fused in the same pass over a tile of 64 points.
+//
+// One persistent CTA per SM walks 64-point tiles.  Per hidden GEMM layer the three contractions
+//   forward  Z_c   = A_c   W^T      (M = 64 points, N = 64 units, K = 64 units)
+//   dgrad    Ab_c  = Zb_c  W        (same shape, B operand = the same W tile viewed MN-major)
+//   wgrad    gW   += Zb_c^T A_c     (M = N = 64 units, K = 64 points, both operands MN-major views)
+// are tcgen05.mma kind::f16 instructions with UMMA M = 64 accumulators in TMEM; the sin/tanh chain
+// rule, the bf16 hi/lo split and the swizzled operand-tile stores are the SIMT epilogue, which
+// reads the accumulators with tcgen05.ld.16x256b (thread = 2 points x 2 units, all channels).
+// Pre-activation jets needed by the reverse sweep are stashed in an L2-resident per-CTA scratch.
+// Parameter gradients (weights and biases of every layer) accumulate in TMEM across all tiles
+// of the CTA and are written once, as a per-CTA partial vector that reduce_kernel sums in fixed order.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pde_launch.h"
 #include "pde_tc.h"
+#include "pde_tc_core.cuh"
+
 namespace pde {
-bool tc_supported(const pde_net*, const pde_program*, long long) { return false; }
-int tc_workspace_bytes(const pde_net*, int, long long, size_t*) { return PDE_ERR_UNSUPPORTED; }
-int tc_residual_loss_grad(const pde_net*, const pde_envelope*, const pde_program*, const void*, long long, const void*,
-                          double, void*, void*, void*, void*, size_t, cudaStream_t) {
-  return PDE_ERR_UNSUPPORTED;
+namespace tc {
+
+constexpr int TP = 64;        // points per tile = UMMA M
+constexpr int HP = 64;        // padded hidden width = UMMA N / K
+constexpr int NWARPS = 8;     // epilogue warps: quarter q = w % 4 (16 points), column half h = w / 4
+constexpr int NTHREADS = NWARPS * 32;
+constexpr int MAXC = 6;       // jet channels the TMEM / smem budget covers
+constexpr int COL_R0 = 0;     // TMEM columns: activation / adjoint accumulators (3 interleaved pairs)
+constexpr int COL_G = 384;    // gW accumulators: slot s at column COL_G + 64 (s / 2), lane half s % 2
+constexpr int COL_SMALL = 448;  // (slot 3) small accumulators, lane half 1: gW0|gb0 at +0, gb_l at +8 l
+
+struct TcArgs {
+  int n_h, act, H;
+  const float* params;          // fp32: W0t [D][64], b [n_h][64], wL [64], bL
+  const unsigned char* wimg;    // per GEMM layer l = 1..n_h-1: hi tile, lo tile (swizzled bf16, rows o, cols i)
+  const float* X;
+  long long n;
+  int num_tiles;
+  int prog, n_q, want_grad;
+  EnvDev<float> env;
+  float alpha, beta_const, energy_const, inv_n;
+  const float* f;
+  const float* beta;
+  const float* energy;
+  const float* seed;
+  float* partial;               // [grid][PP]
+  double* psums;                // [grid][8]
+  float4* stash;                // [grid][stash_f4]
+  long long PP, stash_f4, off_gW0, off_gb0, off_gW, off_gwL, off_gbL;
+};
+
+// ---------------------------------------------------------------- per-element math
+// activation derivatives from the two stashed values (sin: (s, c); tanh: (t, 1 - t^2))
+__device__ __forceinline__ void act_from_stash(int act, float v0, float v1, float& s0, float& s1, float& s2, float& s3) {
+  if (act == 0) {
+    s0 = v0; s1 = v1; s2 = -v0; s3 = -v1;
+  } else {
+    s0 = v0; s1 = v1; s2 = -2.f * v0 * v1; s3 = -2.f * v1 * (1.f - 3.f * v0 * v0);
+  }
 }
+__device__ __forceinline__ void act_eval(int act, float z, float& v0, float& v1) {
+  if (act == 0) {
+    sincosf(z, &v0, &v1);
+  } else {
+    v0 = tanhf(z); v1 = 1.f - v0 * v0;
+  }
+}
+
+// write the (hi, lo) bf16 pairs of two adjacent units of one row into channel c of a tile set
+__device__ __forceinline__ void store_pair(unsigned char* set, int c, int row, int u0, float x0, float x1) {
+  uint32_t hi, lo;
+  split2(x0, x1, hi, lo);
+  const uint32_t off = tile_off(row, u0 >> 3) + ((u0 & 7) << 1);
+  *reinterpret_cast<uint32_t*>(set + (2 * c) * TILE_BYTES + off) = hi;
+  *reinterpret_cast<uint32_t*>(set + (2 * c + 1) * TILE_BYTES + off) = lo;
+}
+
+// ---------------------------------------------------------------- envelope + residual program on (value, grad, Lap) jets
+// nj: network jets in, cotangents out.  Follows program_point in pde_simt.cuh with the Hessian
+// diagonal replaced by its sum.
+template <int D, int ORDER>
+__device__ void program_point_lap(const TcArgs& a, const float* x, long long gp, float (&nj)[1 + (ORDER >= 1 ? D : 0) + (ORDER == 2)],
+                                  double (&qs)[4], double& gE) {
+  constexpr int ND = (ORDER >= 1) ? D : 0;
+  float b[D], b1[D], b2[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) envelope_factor<float>(a.env, i, x[i], b[i], b1[i], b2[i]);
+  float B = 1.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) B *= b[i];
+  float Bi[D], LB = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    float e = 1.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (j != i) e *= b[j];
+    Bi[i] = b1[i] * e;
+    LB += b2[i] * e;
+  }
+  const float N0 = nj[0];
+  const float u = B * N0;
+  float ui[D];
+  float lap = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) ui[i] = 0.f;
+  if constexpr (ORDER >= 1) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) ui[i] = Bi[i] * N0 + B * nj[1 + i];
+  }
+  if constexpr (ORDER == 2) {
+    lap = LB * N0 + B * nj[1 + ND];
+#pragma unroll
+    for (int i = 0; i < D; ++i) lap += 2.f * Bi[i] * nj[1 + i];
+  }
+  const float fv = a.f ? a.f[gp] : 0.f;
+  const float bt = a.beta ? a.beta[gp] : a.beta_const;
+  const float E = a.energy ? a.energy[0] : a.energy_const;
+  const float w0 = (a.seed ? a.seed[0] : 1.f) * a.inv_n;
+  float ub = 0.f, lapb = 0.f, uib[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) uib[i] = 0.f;
+  if (a.prog == PDE_PROG_PINN) {
+    const float r = a.alpha * lap + (bt - E) * u - fv;
+    qs[0] += (double)(r * r);
+    const float rb = 2.f * r * w0;
+    ub = (bt - E) * rb;
+    lapb = a.alpha * rb;
+    gE += (double)(-u * rb);
+  } else if (a.prog == PDE_PROG_DRM) {
+    float g2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) g2 += ui[i] * ui[i];
+    qs[0] += (double)(a.alpha * g2 - fv * u);
+    ub = -fv * w0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) uib[i] = 2.f * a.alpha * ui[i] * w0;
+  } else if (a.prog == PDE_PROG_RAYLEIGH) {
+    float g2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < D; ++i) g2 += ui[i] * ui[i];
+    qs[0] += (double)(a.alpha * g2 + bt * u * u);
+    qs[1] += (double)(u * u);
+    const float w1 = (a.seed ? a.seed[1] : 1.f) * a.inv_n;
+    ub = 2.f * bt * u * w0 + 2.f * u * w1;
+#pragma unroll
+    for (int i = 0; i < D; ++i) uib[i] = 2.f * a.alpha * ui[i] * w0;
+  } else {
+    const float r = u - fv;
+    qs[0] += (double)(r * r);
+    ub = 2.f * r * w0;
+  }
+  float n0b = B * ub;
+  if constexpr (ORDER >= 1) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      n0b += Bi[i] * uib[i];
+      float t = B * uib[i];
+      if constexpr (ORDER == 2) t += 2.f * Bi[i] * lapb;
+      nj[1 + i] = t;
+    }
+  }
+  if constexpr (ORDER == 2) {
+    n0b += LB * lapb;
+    nj[1 + ND] = B * lapb;
+  }
+  nj[0] = n0b;
+}
+
+// ---------------------------------------------------------------- shared-memory carve-up (bytes, after 1024-alignment)
+template <int D, int C>
+struct SmemMap {
+  static constexpr int set_bytes = 2 * C * TILE_BYTES;
+  static constexpr int off_T1 = 0;                        // activations A_l (operand of fwd / wgrad)
+  static constexpr int off_T2 = off_T1 + set_bytes;       // adjoints Zb_l (operand of dgrad / wgrad)
+  static constexpr int off_W = off_T2 + set_bytes;        // W_l hi, lo
+  static constexpr int off_XT = off_W + 2 * TILE_BYTES;   // x^T hi, lo (8 rows x 128 B each), rows j<D: x_j, row D: ones
+  static constexpr int off_E = off_XT + 2048;             // indicator tiles E_0..E_{D-1}: row n all ones
+  static constexpr int off_par = off_E + 1024 * (D > 0 ? D : 1);   // fp32 W0t [D][64], b [4][64], wL [64], bL(+pad)
+  static constexpr int par_floats = D * 64 + 4 * 64 + 64 + 4;
+  static constexpr int off_X = off_par + par_floats * 4;  // X tile [64][D]
+  static constexpr int off_nb = off_X + 64 * D * 4;       // cotangents of the network jets [64][C]
+  static constexpr int off_red = off_nb + 64 * C * 4;     // output-layer partial sums [2][64][C]
+  static constexpr int off_bar = off_red + 2 * 64 * C * 4;
+  static constexpr int total = off_bar + 64;
+};
+
+// ---------------------------------------------------------------- the kernel
+template <int D, int ORDER>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
+  constexpr int ND = (ORDER >= 1) ? D : 0;
+  constexpr int LAP = (ORDER == 2) ? 1 : 0;
+  constexpr int C = 1 + ND + LAP;
+  constexpr int NV = 2 + ND + LAP;  // stashed values per (point, unit, layer)
+  static_assert(C <= MAXC, "too many jet channels for the TMEM / smem budget");
+  using SM = SmemMap<D, C>;
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* T1 = sm + SM::off_T1;
+  unsigned char* T2 = sm + SM::off_T2;
+  unsigned char* WT = sm + SM::off_W;
+  unsigned char* XT = sm + SM::off_XT;
+  unsigned char* ET = sm + SM::off_E;
+  float* sPar = reinterpret_cast<float*>(sm + SM::off_par);
+  float* sW0t = sPar;                 // [D][64]
+  float* sB = sPar + D * 64;          // [4][64]
+  float* sWL = sB + 4 * 64;           // [64], then bL
+  float* sX = reinterpret_cast<float*>(sm + SM::off_X);
+  float* sNb = reinterpret_cast<float*>(sm + SM::off_nb);
+  float* sRed = reinterpret_cast<float*>(sm + SM::off_red);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SM::off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM::off_bar + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;   // this thread's two points (tile rows)
+  const int cq = 2 * (lane & 3);                      // column offset inside an 8-column block
+  const int n_h = a.n_h, act = a.act;
+  const bool do_bwd = a.want_grad != 0;
+  float* part = a.partial + (long long)blockIdx.x * a.PP;
+  float4* stash = a.stash + (long long)blockIdx.x * a.stash_f4;
+
+  // ---- one-time setup
+  for (int i = tid; i < D * 64 + n_h * 64; i += NTHREADS) {
+    // W0t and biases are contiguous in params for n_h layers; smem keeps 4 bias rows
+    sPar[i] = a.params[i];
+  }
+  for (int i = tid; i < 64 + 1; i += NTHREADS) sWL[i] = a.params[D * 64 + n_h * 64 + i];
+  // indicator tiles: E_n has row n all ones (bf16 1.0 = 0x3F80), others zero; X^T lo tile row D zero
+  for (int i = tid; i < (1024 * (D > 0 ? D : 1)) / 4; i += NTHREADS) {
+    const int n = i / 256, w = i % 256;  // tile n, 32-bit word w: row = w / 32
+    reinterpret_cast<uint32_t*>(ET)[i] = ((w >> 5) == n) ? 0x3F803F80u : 0u;
+  }
+  for (int i = tid; i < 512; i += NTHREADS) {
+    const int t = i / 256, w = i % 256;
+    reinterpret_cast<uint32_t*>(XT)[i] = (t == 0 && (w >> 5) == D) ? 0x3F803F80u : 0u;
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  uint32_t phase = 0;
+
+  const uint32_t sT1 = smem_u32(T1), sT2 = smem_u32(T2), sWT = smem_u32(WT), sXT = smem_u32(XT), sET = smem_u32(ET);
+  constexpr uint32_t ID_FWD = make_idesc(64, 64, 0, 0);   // A K-major, B K-major
+  constexpr uint32_t ID_DG = make_idesc(64, 64, 0, 1);    // A K-major, B MN-major (W viewed as W^T)
+  constexpr uint32_t ID_WG = make_idesc(64, 64, 1, 1);    // A, B MN-major (contraction over points)
+  constexpr uint32_t ID_SM = make_idesc(64, 8, 1, 0);     // A MN-major, B K-major, N = 8
+
+  double qs[4] = {0.0, 0.0, 0.0, 0.0};
+  double gE = 0.0;
+  float gwl[4][2];   // output-layer weight gradient partials of this thread's columns
+#pragma unroll
+  for (int j = 0; j < 4; ++j) gwl[j][0] = gwl[j][1] = 0.f;
+  float gbl = 0.f;   // output bias gradient partial (program threads)
+  bool first_tile = true;
+
+  auto load_W = [&](int l) {   // GEMM layer l (1..n_h-1) -> WT
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg + (size_t)(l - 1) * 2 * TILE_BYTES);
+    uint4* dst = reinterpret_cast<uint4*>(WT);
+#pragma unroll
+    for (int i = 0; i < (2 * TILE_BYTES / 16) / NTHREADS; ++i) dst[tid + i * NTHREADS] = src[tid + i * NTHREADS];
+  };
+  // accumulator address of jet channel c: pair c/2 at columns 64 (c/2), lane half c%2
+  auto d_addr = [&](int c) { return taddr_of(tmem, 16 * (c & 1), COL_R0 + 64 * (c >> 1)); };
+  // all threads: make generic smem writes visible to the tensor core, then hand over to the issuer
+  auto sync_to_mma = [&]() {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+  };
+  auto stash_idx = [&](int l, int j, int v) { return (((l * 4 + j) * NWARPS + warp) * NV + v) * 32 + lane; };
+
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const long long base = (long long)tile * TP;
+    // ---- points of this tile; x^T operand tile for the first-layer weight gradient
+    for (int i = tid; i < TP * D; i += NTHREADS) {
+      const long long gp = base + i / D;
+      sX[i] = (gp < a.n) ? a.X[gp * D + (i % D)] : 0.f;
+    }
+    __syncthreads();
+    if (do_bwd) {
+      for (int i = tid; i < D * 32; i += NTHREADS) {
+        const int j = i / 32, pp = 2 * (i % 32);   // row j of X^T, points pp, pp+1
+        uint32_t hi, lo;
+        split2(sX[pp * D + j], sX[(pp + 1) * D + j], hi, lo);
+        const uint32_t off = tile_off(j, pp >> 3) + ((pp & 7) << 1);
+        *reinterpret_cast<uint32_t*>(XT + off) = hi;
+        *reinterpret_cast<uint32_t*>(XT + 1024 + off) = lo;
+      }
+    }
+
+    float outacc[2][C];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < C; ++c) outacc[r][c] = 0.f;
+
+    // ================= forward =================
+    for (int l = 0; l < n_h; ++l) {
+      if (l >= 1) {
+        load_W(l);
+        sync_to_mma();
+        if (warp == 0) {
+          if (lane == 0) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+              const uint32_t d = d_addr(c);
+              uint32_t acc = 0;
+#pragma unroll 1
+              for (int t = 0; t < 3; ++t) {
+                const uint32_t at = sT1 + (2 * c + (t == 1 ? 1 : 0)) * TILE_BYTES;
+                const uint32_t bt = sWT + (t == 2 ? TILE_BYTES : 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  mma_bf16(d, desc_kmajor(at, ks), desc_kmajor(bt, ks), ID_FWD, acc);
+                  acc = 1;
+                }
+              }
+            }
+            mma_commit(bar);
+          }
+          __syncwarp();
+        }
+        wait_mma();
+      }
+      const bool last = (l == n_h - 1);
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int u0 = 16 * j + 8 * h + cq;   // this thread's columns u0, u0+1
+        float z[C][4];                        // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]
+        if (l == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int row = (e < 2) ? r0 : r1, u = u0 + (e & 1);
+            float v = sB[u];
+#pragma unroll
+            for (int jd = 0; jd < D; ++jd) v = fmaf(sW0t[jd * 64 + u], sX[row * D + jd], v);
+            z[0][e] = v;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) z[1 + i][e] = sW0t[i * 64 + u];
+            if constexpr (LAP) z[1 + ND][e] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(c) + ((32 * q) << 16) + 16 * j + 8 * h, z[c]);
+          tmem_ld_wait();
+          const float b0v = sB[l * 64 + u0], b1v = sB[l * 64 + u0 + 1];
+          z[0][0] += b0v; z[0][1] += b1v; z[0][2] += b0v; z[0][3] += b1v;
+        }
+        float av[C][4], sv0[4], sv1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          act_eval(act, z[0][e], sv0[e], sv1[e]);
+          float s0, s1, s2, s3;
+          act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
+          av[0][e] = s0;
+          float S = 0.f;
+#pragma unroll
+          for (int i = 0; i < ND; ++i) {
+            av[1 + i][e] = s1 * z[1 + i][e];
+            S = fmaf(z[1 + i][e], z[1 + i][e], S);
+          }
+          if constexpr (LAP) av[1 + ND][e] = fmaf(s1, z[1 + ND][e], s2 * S);
+        }
+        if (do_bwd) {
+          stash[stash_idx(l, j, 0)] = make_float4(sv0[0], sv0[1], sv0[2], sv0[3]);
+          stash[stash_idx(l, j, 1)] = make_float4(sv1[0], sv1[1], sv1[2], sv1[3]);
+          if (l >= 1) {
+#pragma unroll
+            for (int c = 1; c < C; ++c) stash[stash_idx(l, j, 1 + c)] = make_float4(z[c][0], z[c][1], z[c][2], z[c][3]);
+          }
+        }
+        if (!last) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            store_pair(T1, c, r0, u0, av[c][0], av[c][1]);
+            store_pair(T1, c, r1, u0, av[c][2], av[c][3]);
+          }
+        } else {
+          const float w0v = sWL[u0], w1v = sWL[u0 + 1];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            outacc[0][c] = fmaf(w0v, av[c][0], fmaf(w1v, av[c][1], outacc[0][c]));
+            outacc[1][c] = fmaf(w0v, av[c][2], fmaf(w1v, av[c][3], outacc[1][c]));
+          }
+        }
+      }
+    }
+
+    // ================= output layer + envelope + residual program =================
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v = outacc[r][c];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        outacc[r][c] = v;
+      }
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        sRed[(h * 64 + r0) * C + c] = outacc[0][c];
+        sRed[(h * 64 + r1) * C + c] = outacc[1][c];
+      }
+    }
+    __syncthreads();
+    if (tid < TP) {
+      const long long gp = base + tid;
+      float nj[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) nj[c] = sRed[tid * C + c] + sRed[(64 + tid) * C + c];
+      nj[0] += sWL[64];
+      if (gp < a.n) {
+        program_point_lap<D, ORDER>(a, sX + tid * D, gp, nj, qs, gE);
+        gbl += nj[0];
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) nj[c] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) sNb[tid * C + c] = nj[c];
+    }
+    __syncthreads();
+    if (!do_bwd) continue;
+
+    // ================= reverse sweep =================
+    for (int l = n_h - 1; l >= 0; --l) {
+      const bool top = (l == n_h - 1);
+      if (l >= 1) load_W(l);   // the previous MMAs reading WT have completed (wait_mma)
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        const int u0 = 16 * j + 8 * h + cq;
+        float ab[C][4];
+        if (top) {
+          const float w0v = sWL[u0], w1v = sWL[u0 + 1];
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float n0 = sNb[r0 * C + c], n1 = sNb[r1 * C + c];
+            ab[c][0] = w0v * n0; ab[c][1] = w1v * n0; ab[c][2] = w0v * n1; ab[c][3] = w1v * n1;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(c) + ((32 * q) << 16) + 16 * j + 8 * h, ab[c]);
+          tmem_ld_wait();
+        }
+        // stash of this layer: activation values and pre-activation jets
+        const float4 q0 = stash[stash_idx(l, j, 0)], q1 = stash[stash_idx(l, j, 1)];
+        const float sv0[4] = {q0.x, q0.y, q0.z, q0.w}, sv1[4] = {q1.x, q1.y, q1.z, q1.w};
+        float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
+        if (l >= 1) {
+#pragma unroll
+          for (int c = 1; c < C; ++c) {
+            const float4 t = stash[stash_idx(l, j, 1 + c)];
+            zj[c][0] = t.x; zj[c][1] = t.y; zj[c][2] = t.z; zj[c][3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int u = u0 + (e & 1);
+#pragma unroll
+            for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[i * 64 + u];
+            if constexpr (LAP) zj[1 + ND][e] = 0.f;
+          }
+        }
+        float zb[C][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float s0, s1, s2, s3;
+          act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
+          float t0 = s1 * ab[0][e];
+          float abL = 0.f;
+          if constexpr (LAP) abL = ab[1 + ND][e];
+          float S = 0.f;
+#pragma unroll
+          for (int i = 0; i < ND; ++i) {
+            const float zi = zj[1 + i][e];
+            t0 = fmaf(s2 * zi, ab[1 + i][e], t0);
+            S = fmaf(zi, zi, S);
+            float ti = s1 * ab[1 + i][e];
+            if constexpr (LAP) ti = fmaf(2.f * s2 * zi, abL, ti);
+            zb[1 + i][e] = ti;
+          }
+          if constexpr (LAP) {
+            t0 = fmaf(fmaf(s2, zj[1 + ND][e], s3 * S), abL, t0);
+            zb[1 + ND][e] = s1 * abL;
+          }
+          zb[0][e] = t0;
+          if (top) {
+            // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
+            const int r = (e < 2) ? r0 : r1;
+            float g = sNb[r * C] * s0;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) g = fmaf(sNb[r * C + 1 + i], s1 * zj[1 + i][e], g);
+            if constexpr (LAP) g = fmaf(sNb[r * C + 1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
+            gwl[j][e & 1] += g;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          store_pair(T2, c, r0, u0, zb[c][0], zb[c][1]);
+          store_pair(T2, c, r1, u0, zb[c][2], zb[c][3]);
+        }
+        if (l >= 1) {
+          // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
+          const float4 p0 = stash[stash_idx(l - 1, j, 0)], p1 = stash[stash_idx(l - 1, j, 1)];
+          const float pv0[4] = {p0.x, p0.y, p0.z, p0.w}, pv1[4] = {p1.x, p1.y, p1.z, p1.w};
+          float zp[C][4];
+          if (l - 1 >= 1) {
+#pragma unroll
+            for (int c = 1; c < C; ++c) {
+              const float4 t = stash[stash_idx(l - 1, j, 1 + c)];
+              zp[c][0] = t.x; zp[c][1] = t.y; zp[c][2] = t.z; zp[c][3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int u = u0 + (e & 1);
+#pragma unroll
+              for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
+              if constexpr (LAP) zp[1 + ND][e] = 0.f;
+            }
+          }
+          float ap[C][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float s0, s1, s2, s3;
+            act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
+            ap[0][e] = s0;
+            float S = 0.f;
+#pragma unroll
+            for (int i = 0; i < ND; ++i) {
+              ap[1 + i][e] = s1 * zp[1 + i][e];
+              S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
+            }
+            if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            store_pair(T1, c, r0, u0, ap[c][0], ap[c][1]);
+            store_pair(T1, c, r1, u0, ap[c][2], ap[c][3]);
+          }
+        }
+      }
+      sync_to_mma();
+      if (warp == 0) {
+        if (lane == 0) {
+          tc_fence_after();
+          if (l >= 1) {
+            // dgrad: Ab_{l-1,c} = Zb_{l,c} W_l
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+              const uint32_t d = d_addr(c);
+              uint32_t acc = 0;
+#pragma unroll 1
+              for (int t = 0; t < 3; ++t) {
+                const uint32_t at = sT2 + (2 * c + (t == 1 ? 1 : 0)) * TILE_BYTES;
+                const uint32_t bt = sWT + (t == 2 ? TILE_BYTES : 0);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  mma_bf16(d, desc_kmajor(at, ks), desc_mnmajor(bt, ks), ID_DG, acc);
+                  acc = 1;
+                }
+              }
+            }
+            // wgrad: gW_l += sum_c Zb_{l,c}^T A_{l-1,c}
+            {
+              const int sl = l - 1;
+              const uint32_t d = taddr_of(tmem, 16 * (sl & 1), COL_G + 64 * (sl >> 1));
+              uint32_t acc = first_tile ? 0u : 1u;
+#pragma unroll 1
+              for (int c = 0; c < C; ++c) {
+#pragma unroll 1
+                for (int t = 0; t < 3; ++t) {
+                  const uint32_t at = sT2 + (2 * c + (t == 1 ? 1 : 0)) * TILE_BYTES;
+                  const uint32_t bt = sT1 + (2 * c + (t == 2 ? 1 : 0)) * TILE_BYTES;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    mma_bf16(d, desc_mnmajor(at, ks), desc_mnmajor(bt, ks), ID_WG, acc);
+                    acc = 1;
+                  }
+                }
+              }
+            }
+            // bias: gb_l += Zb_{l,0}^T 1
+            {
+              const uint32_t d = taddr_of(tmem, 16, COL_SMALL + 8 * l);
+              uint32_t acc = first_tile ? 0u : 1u;
+#pragma unroll 1
+              for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  mma_bf16(d, desc_mnmajor(sT2 + t * TILE_BYTES, ks), desc_kmajor(sET, ks), ID_SM, acc);
+                  acc = 1;
+                }
+              }
+            }
+          } else {
+            // first layer: [gW0 | gb0] += Zb_{0,0}^T [x | 1] + sum_i Zb_{0,i}^T e_i
+            const uint32_t d = taddr_of(tmem, 16, COL_SMALL);
+            uint32_t acc = first_tile ? 0u : 1u;
+#pragma unroll 1
+            for (int t = 0; t < 3; ++t) {
+              const uint32_t at = sT2 + (t == 1 ? 1 : 0) * TILE_BYTES;
+              const uint32_t bt = sXT + (t == 2 ? 1024 : 0);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_bf16(d, desc_mnmajor(at, ks), desc_kmajor(bt, ks), ID_SM, acc);
+                acc = 1;
+              }
+            }
+#pragma unroll 1
+            for (int i = 0; i < ND; ++i) {
+#pragma unroll 1
+              for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  mma_bf16(d, desc_mnmajor(sT2 + (2 * (1 + i) + t) * TILE_BYTES, ks), desc_kmajor(sET + 1024 * i, ks), ID_SM, 1u);
+              }
+            }
+          }
+          mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      wait_mma();
+    }
+    first_tile = false;
+  }
+
+  // ================= per-CTA results =================
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (do_bwd) {
+    // hidden GEMM layers: gW_l at slot l-1, rows o = 16 q + lane/4 (+8), columns i
+    for (int l = 1; l < n_h; ++l) {
+      const int sl = l - 1;
+      float* gW = part + a.off_gW + (long long)sl * ((long long)HP * HP + HP);
+      const uint32_t d = taddr_of(tmem, 32 * q + 16 * (sl & 1), COL_G + 64 * (sl >> 1));
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float v[4];
+        tmem_ld_16x256b(d + 32 * h + 8 * b, v);
+        tmem_ld_wait();
+        const int i0 = 32 * h + 8 * b + cq;
+        *reinterpret_cast<float2*>(gW + r0 * HP + i0) = make_float2(v[0], v[1]);
+        *reinterpret_cast<float2*>(gW + r1 * HP + i0) = make_float2(v[2], v[3]);
+      }
+      if (h == 0) {
+        float v[4];
+        tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL + 8 * l), v);
+        tmem_ld_wait();
+        if ((lane & 3) == 0) {
+          gW[HP * HP + r0] = v[0];
+          gW[HP * HP + r1] = v[2];
+        }
+      }
+    }
+    if (h == 0) {
+      float v[4];
+      tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL), v);
+      tmem_ld_wait();
+      // columns cq, cq+1 of [gW0 (D cols) | gb0]
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = cq + (e & 1), o = (e < 2) ? r0 : r1;
+        if (col < D) part[a.off_gW0 + o * D + col] = v[e];
+        else if (col == D) part[a.off_gb0 + o] = v[e];
+      }
+    }
+    // output layer: reduce the per-thread column partials over the 8 row groups of the warp ...
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float v = gwl[j][k];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        gwl[j][k] = v;
+      }
+    float* sRedW = sRed;   // [4 quarters][64 columns]
+    if (lane < 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sRedW[q * 64 + 16 * j + 8 * h + cq] = gwl[j][0];
+        sRedW[q * 64 + 16 * j + 8 * h + cq + 1] = gwl[j][1];
+      }
+    }
+    __syncthreads();
+    // ... then over the four quarters in fixed order
+    if (tid < 64) part[a.off_gwL + tid] = (sRedW[tid] + sRedW[64 + tid]) + (sRedW[128 + tid] + sRedW[192 + tid]);
+    __syncthreads();
+    float* sRedB = sRed;
+    if (tid < 64) sRedB[tid] = gbl;
+    __syncthreads();
+    if (tid == 0) {
+      float v = 0.f;
+      for (int i = 0; i < 64; ++i) v += sRedB[i];
+      part[a.off_gbL] = v;
+    }
+    __syncthreads();
+  }
+  {
+    double* dred = reinterpret_cast<double*>(T1);   // 64 x 5 doubles
+    if (tid < TP) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dred[tid * 5 + k] = qs[k];
+      dred[tid * 5 + 4] = gE;
+    }
+    __syncthreads();
+    if (tid < 5) {
+      double v = 0.0;
+      for (int pp = 0; pp < TP; ++pp) v += dred[pp * 5 + tid];
+      a.psums[(long long)blockIdx.x * 8 + tid] = v;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------- parameter images
+struct TcPackArgs {
+  const float* W[PDE_MAX_LINEAR];
+  const float* b[PDE_MAX_LINEAR];
+  int n_lin, D, H;
+  float* params;           // W0t [D][64], b [n_h][64], wL [64], bL
+  unsigned char* wimg;     // [(n_h-1)][2][8192]
+};
+
+__global__ void tc_pack_kernel(const TcPackArgs a) {
+  const int n_h = a.n_lin - 1;
+  const int n_par = a.D * 64 + n_h * 64 + 64 + 1;
+  const int n_img = (n_h - 1) * 64 * 32;   // pairs of adjacent columns
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_par + n_img; i += gridDim.x * blockDim.x) {
+    if (i < n_par) {
+      float v = 0.f;
+      if (i < a.D * 64) {
+        const int j = i / 64, u = i % 64;
+        if (u < a.H) v = a.W[0][u * a.D + j];
+      } else if (i < a.D * 64 + n_h * 64) {
+        const int r = i - a.D * 64, l = r / 64, u = r % 64;
+        if (u < a.H) v = a.b[l][u];
+      } else if (i < a.D * 64 + n_h * 64 + 64) {
+        const int u = i - a.D * 64 - n_h * 64;
+        if (u < a.H) v = a.W[n_h][u];
+      } else {
+        v = a.b[n_h][0];
+      }
+      a.params[i] = v;
+    } else {
+      const int r = i - n_par, l = r / (64 * 32) + 1, e = r % (64 * 32), o = e / 32, i0 = 2 * (e % 32);
+      float x0 = 0.f, x1 = 0.f;
+      if (o < a.H) {
+        if (i0 < a.H) x0 = a.W[l][o * a.H + i0];
+        if (i0 + 1 < a.H) x1 = a.W[l][o * a.H + i0 + 1];
+      }
+      uint32_t hi, lo;
+      split2(x0, x1, hi, lo);
+      unsigned char* img = a.wimg + (size_t)(l - 1) * 2 * TILE_BYTES;
+      const uint32_t off = tile_off(o, i0 >> 3) + ((i0 & 7) << 1);
+      *reinterpret_cast<uint32_t*>(img + off) = hi;
+      *reinterpret_cast<uint32_t*>(img + TILE_BYTES + off) = lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+struct TcPlan {
+  int D, order, C, NV, n_lin, n_h, H, grid, num_tiles, sms;
+  size_t smem_bytes;
+  long long PP, off_gW0, off_gb0, off_gW, off_gwL, off_gbL, n_params, stash_f4;
+  size_t ws_params, ws_wimg, ws_partial, ws_psums, ws_stash, ws_total;
+};
+
+static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
+
+template <int D, int ORDER>
+static cudaError_t launch_one(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
+  constexpr int C = 1 + (ORDER >= 1 ? D : 0) + (ORDER == 2);
+  if constexpr (C > MAXC) {
+    return cudaErrorInvalidValue;
+  } else {
+    const int smem = SmemMap<D, C>::total + 1024;
+    cudaError_t err = cudaFuncSetAttribute(tc_kernel<D, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    tc_kernel<D, ORDER><<<p.grid, NTHREADS, smem, st>>>(a);
+    return cudaGetLastError();
+  }
+}
+
+static cudaError_t launch_tc(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
+  switch (p.D * 3 + p.order) {
+    case 3: return launch_one<1, 0>(p, a, st);
+    case 4: return launch_one<1, 1>(p, a, st);
+    case 5: return launch_one<1, 2>(p, a, st);
+    case 6: return launch_one<2, 0>(p, a, st);
+    case 7: return launch_one<2, 1>(p, a, st);
+    case 8: return launch_one<2, 2>(p, a, st);
+    case 9: return launch_one<3, 0>(p, a, st);
+    case 10: return launch_one<3, 1>(p, a, st);
+    case 11: return launch_one<3, 2>(p, a, st);
+    case 12: return launch_one<4, 0>(p, a, st);
+    case 13: return launch_one<4, 1>(p, a, st);
+    case 14: return launch_one<4, 2>(p, a, st);
+    case 15: return launch_one<5, 0>(p, a, st);
+    case 16: return launch_one<5, 1>(p, a, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+static int path_override() {
+  // PDE_B200_PATH=simt|tc forces one kernel family (used by the parity tests); default: tc where supported
+  const char* e = getenv("PDE_B200_PATH");
+  return !e ? -1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc") == 0 ? 1 : -1));
+}
+
+static bool shape_ok(const pde_net* net, int order, long long n) {
+  if (!net || net->dtype != PDE_F32) return false;
+  if (net->dim < 1 || net->dim > PDE_MAX_DIM) return false;
+  const int n_h = net->n_linear - 1;
+  if (n_h < 2 || n_h > 4) return false;
+  const int H = net->widths[1];
+  if (H < 1 || H > HP) return false;
+  for (int l = 1; l < net->n_linear; ++l)
+    if (net->widths[l] != H) return false;
+  if (net->widths[0] != net->dim || net->widths[net->n_linear] != 1) return false;
+  if (order < 0 || order > 2) return false;
+  const int C = 1 + (order >= 1 ? net->dim : 0) + (order == 2);
+  if (C > MAXC) return false;
+  const int ov = path_override();
+  if (ov == 0) return false;
+  if (ov == 1) return n >= 1;
+  return n >= 4096;   // below that the launch is latency bound and the generic kernel is as fast
+}
+
+static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl) {
+  if (!shape_ok(net, order, n)) return PDE_ERR_UNSUPPORTED;
+  static int sms_cached = 0;
+  if (!sms_cached) {
+    int dev = 0, sms = 0, cc = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return PDE_ERR_NO_DEVICE; }
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return PDE_ERR_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return PDE_ERR_NO_DEVICE;
+    if (cc != 10) return PDE_ERR_UNSUPPORTED;
+    sms_cached = sms;
+  }
+  TcPlan& p = *pl;
+  memset(&p, 0, sizeof(p));
+  p.sms = sms_cached;
+  p.D = net->dim; p.order = order;
+  p.C = 1 + (order >= 1 ? p.D : 0) + (order == 2);
+  p.NV = 1 + p.C;
+  p.n_lin = net->n_linear; p.n_h = p.n_lin - 1; p.H = net->widths[1];
+  p.num_tiles = (int)((n + TP - 1) / TP);
+  p.grid = p.num_tiles < p.sms ? p.num_tiles : p.sms;
+  const long long HH = (long long)HP * HP;
+  p.off_gW0 = 0;
+  p.off_gb0 = (long long)HP * p.D;
+  p.off_gW = p.off_gb0 + HP;
+  p.off_gwL = p.off_gW + (long long)(p.n_h - 1) * (HH + HP);
+  p.off_gbL = p.off_gwL + HP;
+  p.PP = rup(p.off_gbL + 1, 4);
+  p.n_params = (long long)p.H * p.D + p.H + (long long)(p.n_h - 1) * ((long long)p.H * p.H + p.H) + p.H + 1;
+  p.stash_f4 = (long long)p.n_h * 4 * NWARPS * p.NV * 32;
+  p.ws_params = (size_t)rup((p.D * 64 + p.n_h * 64 + 64 + 1) * 4, 256);
+  p.ws_wimg = (size_t)(p.n_h - 1) * 2 * TILE_BYTES;
+  p.ws_partial = (size_t)rup((long long)p.sms * p.PP * 4, 256);
+  p.ws_psums = (size_t)rup((long long)p.sms * 8 * 8, 256);
+  p.ws_stash = (size_t)rup((long long)p.sms * p.stash_f4 * 16, 256);
+  p.ws_total = p.ws_params + p.ws_wimg + p.ws_partial + p.ws_psums + p.ws_stash;
+  return PDE_OK;
+}
+
+}  // namespace tc
+
+bool tc_supported(const pde_net* net, const pde_program* prog, long long n_points) {
+  if (!prog) return false;
+  const int order = pde_program_order(prog->kind);
+  tc::TcPlan p;
+  return tc::make_plan(net, order, n_points, &p) == PDE_OK;
+}
+
+int tc_workspace_bytes(const pde_net* net, int order, long long n_points, size_t* bytes) {
+  tc::TcPlan p;
+  int rc = tc::make_plan(net, order, n_points, &p);
+  if (rc) return rc;
+  *bytes = p.ws_total;
+  return PDE_OK;
+}
+
+int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
+                          long long n_points, const void* seed, double inv_n, void* sums, void* grad,
+                          void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  using namespace tc;
+  if (!net || !prog) return PDE_ERR_INVALID;
+  const int order = pde_program_order(prog->kind);
+  if (order < 0) return PDE_ERR_INVALID;
+  TcPlan p;
+  int rc = make_plan(net, order, n_points, &p);
+  if (rc) return rc;
+  for (int l = 0; l < p.n_lin; ++l)
+    if (!net->W[l] || !net->b[l]) return PDE_ERR_INVALID;
+  if (!X || !workspace) return PDE_ERR_INVALID;
+  if (workspace_bytes < p.ws_total) return PDE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PDE_ERR_INVALID;
+  unsigned char* wsb = static_cast<unsigned char*>(workspace);
+  float* params = reinterpret_cast<float*>(wsb);
+  unsigned char* wimg = wsb + p.ws_params;
+  float* partial = reinterpret_cast<float*>(wsb + p.ws_params + p.ws_wimg);
+  double* psums = reinterpret_cast<double*>(wsb + p.ws_params + p.ws_wimg + p.ws_partial);
+  float4* stash = reinterpret_cast<float4*>(wsb + p.ws_params + p.ws_wimg + p.ws_partial + p.ws_psums);
+
+  TcPackArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  for (int l = 0; l < p.n_lin; ++l) { pa.W[l] = static_cast<const float*>(net->W[l]); pa.b[l] = static_cast<const float*>(net->b[l]); }
+  pa.n_lin = p.n_lin; pa.D = p.D; pa.H = p.H; pa.params = params; pa.wimg = wimg;
+  tc_pack_kernel<<<32, 256, 0, st>>>(pa);
+  if (cudaGetLastError() != cudaSuccess) return PDE_ERR_CUDA;
+
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_h = p.n_h; a.act = net->activation; a.H = p.H;
+  a.params = params; a.wimg = wimg;
+  a.X = static_cast<const float*>(X); a.n = n_points; a.num_tiles = p.num_tiles;
+  a.prog = prog->kind; a.n_q = pde_program_quantities(prog->kind);
+  a.want_grad = (grad != nullptr) || (energy_grad != nullptr);
+  if (env) {
+    a.env.kind = env->kind; a.env.lo = (float)env->lo; a.env.hi = (float)env->hi;
+    for (int i = 0; i < PDE_MAX_DIM; ++i) {
+      a.env.n_nodes[i] = env->n_nodes[i];
+      for (int k = 0; k < PDE_MAX_NODES; ++k) a.env.nodes[i][k] = (float)env->nodes[i][k];
+    }
+  }
+  a.alpha = (float)prog->alpha; a.beta_const = (float)prog->beta_const; a.energy_const = (float)prog->energy_const;
+  a.inv_n = (float)inv_n;
+  a.f = static_cast<const float*>(prog->f); a.beta = static_cast<const float*>(prog->beta);
+  a.energy = static_cast<const float*>(prog->energy); a.seed = static_cast<const float*>(seed);
+  a.partial = partial; a.psums = psums; a.stash = stash;
+  a.PP = p.PP; a.stash_f4 = p.stash_f4;
+  a.off_gW0 = p.off_gW0; a.off_gb0 = p.off_gb0; a.off_gW = p.off_gW; a.off_gwL = p.off_gwL; a.off_gbL = p.off_gbL;
+  if (launch_tc(p, a, st) != cudaSuccess) return PDE_ERR_CUDA;
+
+  ReduceArgs<float> r;
+  memset(&r, 0, sizeof(r));
+  r.partial = partial; r.psums = psums; r.PP = p.PP; r.grid = p.grid; r.n_lin = p.n_lin; r.D = p.D; r.H = p.H; r.Hp = HP;
+  r.n_q = a.n_q;
+  r.off_gW0 = p.off_gW0; r.off_gb0 = p.off_gb0; r.off_gW = p.off_gW; r.off_gwL = p.off_gwL; r.off_gbL = p.off_gbL;
+  r.n_params = p.n_params;
+  r.grad = static_cast<float*>(grad);
+  r.sums = static_cast<float*>(sums);
+  r.energy_grad = static_cast<float*>(energy_grad);
+  if (launch_reduce<float>(st, r) != cudaSuccess) return PDE_ERR_CUDA;
+  return PDE_OK;
+}
+
 }  // namespace pde

@@ -27,7 +27,7 @@ def mm(a, b, fmt, mode):
         out = out + A[1] @ B[1]
     return out.astype(np.float32).astype(np.float64)
 
-def run(fmt, mode, N=16384, d=3, seed=0):
+def run(fmt, mode, N=16384, d=3, seed=0, bscale=1.0):
     rng = np.random.default_rng(seed)
     torch.manual_seed(seed)
     import pde_b200  # noqa
@@ -56,7 +56,7 @@ def run(fmt, mode, N=16384, d=3, seed=0):
     U, ctx = O.apply_envelope(J, X, 2, O.ENV_POLY, 0.0, 2.0)
     q, Ub, _ = O.pinn_program(U, d, f, alpha=-1.0)
     loss = q.mean()
-    Jb = O.envelope_backward(Ub / N, ctx, 2, d)
+    Jb = O.envelope_backward(Ub / N * bscale, ctx, 2, d)
     gW = [None] * n; gb = [None] * n
     zb = [Jb[:, c:c + 1] for c in range(C)]
     gW[-1] = sum(zb[c].T @ a[c] for c in range(C)); gb[-1] = zb[0].sum(0)
@@ -78,6 +78,7 @@ def run(fmt, mode, N=16384, d=3, seed=0):
             gW[l] = sum(mm(nz[c].T, ain[c], fmt, mode) for c in range(C))
             ab = [mm(nz[c], Ws[l], fmt, mode) for c in range(C)]
         gb[l] = nz[0].sum(0)
+    gW = [g / bscale for g in gW]; gb = [g / bscale for g in gb]
     gref = np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(rW, rb)])
     gem = np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(gW, gb)])
     per = max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(gW + gb, rW + rb) if np.linalg.norm(b) > 0)
@@ -85,5 +86,5 @@ def run(fmt, mode, N=16384, d=3, seed=0):
           f"  worst tensor {per:.2e}  max-abs/max {np.max(np.abs(gem - gref)) / np.max(np.abs(gref)):.2e}")
 
 if __name__ == "__main__":
-    for fmt, mode in [("bf16", "fp32"), ("bf16", "1"), ("bf16", "3"), ("bf16", "4"), ("fp16", "3")]:
-        run(fmt, mode)
+    for fmt, mode, sc in [("bf16", "3", 1.0), ("fp16", "3", 1.0), ("fp16", "3", 16384.0), ("fp16", "3", 16384.0 * 64)]:
+        print("bscale", sc, end=": "); run(fmt, mode, bscale=sc)
