@@ -34,8 +34,8 @@ namespace tc {
 
 constexpr int TP = 64;        // points per tile = UMMA M
 constexpr int HP = 64;        // padded hidden width = UMMA N / K
-constexpr int NWARPS = 8;     // epilogue warps: quarter q = w % 4 (16 points), column half h = w / 4
-constexpr int NTHREADS = NWARPS * 32;
+constexpr int NEPI = 8;       // epilogue warps: quarter q = w % 4 (16 points), column half h = w / 4
+constexpr int NTHREADS = (NEPI + 1) * 32;   // + one MMA-issuer warp
 constexpr int MAXC = 6;       // jet channels the TMEM / smem budget covers
 constexpr int COL_R0 = 0;     // TMEM columns: activation / adjoint accumulators (3 interleaved pairs)
 constexpr int COL_G = 384;    // gW accumulators: slot s at column COL_G + 64 (s / 2), lane half s % 2
@@ -179,14 +179,16 @@ __device__ void program_point_lap(const TcArgs& a, const float* x, long long gp,
   nj[0] = n0b;
 }
 
-// ---------------------------------------------------------------- shared-memory carve-up (bytes, after 1024-alignment)
+// ---------------------------------------------------------------- shared-memory carve-up (bytes from the 1024-aligned base)
 template <int D, int C>
 struct SmemMap {
+  static constexpr bool w_resident = (C <= 5);            // all hidden W tiles stay in smem when they fit
   static constexpr int set_bytes = 2 * C * TILE_BYTES;
   static constexpr int off_T1 = 0;                        // activations A_l (operand of fwd / wgrad)
   static constexpr int off_T2 = off_T1 + set_bytes;       // adjoints Zb_l (operand of dgrad / wgrad)
-  static constexpr int off_W = off_T2 + set_bytes;        // W_l hi, lo
-  static constexpr int off_XT = off_W + 2 * TILE_BYTES;   // x^T hi, lo (8 rows x 128 B each), rows j<D: x_j, row D: ones
+  static constexpr int off_W = off_T2 + set_bytes;        // W_l hi, lo (x3 layers when resident)
+  static constexpr int w_bytes = (w_resident ? 3 : 1) * 2 * TILE_BYTES;
+  static constexpr int off_XT = off_W + w_bytes;          // x^T hi, lo (8 rows x 128 B each), rows j<D: x_j, row D: ones
   static constexpr int off_E = off_XT + 2048;             // indicator tiles E_0..E_{D-1}: row n all ones
   static constexpr int off_par = off_E + 1024 * (D > 0 ? D : 1);   // fp32 W0t [D][64], b [4][64], wL [64], bL(+pad)
   static constexpr int par_floats = D * 64 + 4 * 64 + 64 + 4;
@@ -194,10 +196,31 @@ struct SmemMap {
   static constexpr int off_nb = off_X + 64 * D * 4;       // cotangents of the network jets [64][C]
   static constexpr int off_red = off_nb + 64 * C * 4;     // output-layer partial sums [2][64][C]
   static constexpr int off_bar = off_red + 2 * 64 * C * 4;
-  static constexpr int total = off_bar + 64;
+  static constexpr int total = off_bar + 128;
 };
 
+// explicit state-space accesses (pointers reached through the argument struct are generic otherwise)
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// UMMA descriptors as "constant high part + 14-bit start address": K-major / MN-major Tile64 views
+constexpr uint64_t DESC_K = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+constexpr uint64_t DESC_MN = (static_cast<uint64_t>(8192 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, int ks) { return DESC_K | static_cast<uint64_t>((saddr >> 4) + 2 * ks); }
+__device__ __forceinline__ uint64_t mdesc(uint32_t saddr, int ks) { return DESC_MN | static_cast<uint64_t>((saddr >> 4) + 128 * ks); }
+
 // ---------------------------------------------------------------- the kernel
+// Warps 0..7: epilogue (quarter q = w % 4 owns points 16q..16q+15, half h = w / 4 owns 8 of the 16
+// columns of a chunk).  Warp 8: one elected thread issues every tcgen05.mma.
+// Hand-offs (all mbarriers, one phase bit each, flipped once per use):
+//   bar_chunk[j]  8 arrivals   epilogue -> issuer : operand columns 16j..16j+15 (= K step j) are in smem
+//   bar_d         commit       issuer -> epilogue : the accumulators the next step reads are complete
+//   bar_w         commit       issuer -> epilogue : every MMA that reads the operand sets has completed
+// Accumulator regions ping-pong (R0/R1) so that the MMAs of step s+1 run while step s is still
+// being read; a step's K-step-j MMAs are issued as soon as chunk j has been written.
 template <int D, int ORDER>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   constexpr int ND = (ORDER >= 1) ? D : 0;
@@ -206,14 +229,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   constexpr int NV = 2 + ND + LAP;  // stashed values per (point, unit, layer)
   static_assert(C <= MAXC, "too many jet channels for the TMEM / smem budget");
   using SM = SmemMap<D, C>;
+  constexpr bool WRES = SM::w_resident;
 
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  unsigned char* T1 = sm + SM::off_T1;
-  unsigned char* T2 = sm + SM::off_T2;
-  unsigned char* WT = sm + SM::off_W;
-  unsigned char* XT = sm + SM::off_XT;
-  unsigned char* ET = sm + SM::off_E;
+  extern __shared__ __align__(1024) unsigned char sm[];
   float* sPar = reinterpret_cast<float*>(sm + SM::off_par);
   float* sW0t = sPar;                 // [D][64]
   float* sB = sPar + D * 64;          // [4][64]
@@ -221,524 +239,581 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   float* sX = reinterpret_cast<float*>(sm + SM::off_X);
   float* sNb = reinterpret_cast<float*>(sm + SM::off_nb);
   float* sRed = reinterpret_cast<float*>(sm + SM::off_red);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + SM::off_bar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM::off_bar + 16);
+  uint64_t* bar_chunk = reinterpret_cast<uint64_t*>(sm + SM::off_bar);   // [4]
+  uint64_t* bar_d = bar_chunk + 4;
+  uint64_t* bar_w = bar_chunk + 5;
+  uint64_t* bar_own = bar_chunk + 6;   // issuer-private: "everything I issued so far has completed"
+  uint64_t* bar_wt = bar_chunk + 7;    // bulk copy of a W tile pair has landed (non-resident W only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_chunk + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3, h = warp >> 2;
-  const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;   // this thread's two points (tile rows)
-  const int cq = 2 * (lane & 3);                      // column offset inside an 8-column block
   const int n_h = a.n_h, act = a.act;
   const bool do_bwd = a.want_grad != 0;
-  float* part = a.partial + (long long)blockIdx.x * a.PP;
-  float4* stash = a.stash + (long long)blockIdx.x * a.stash_f4;
+  const uint32_t sbase = smem_u32(sm);
+  const uint32_t sT1 = sbase + SM::off_T1, sT2 = sbase + SM::off_T2, sWT = sbase + SM::off_W;
+  const uint32_t sXT = sbase + SM::off_XT, sET = sbase + SM::off_E;
 
-  // ---- one-time setup
-  for (int i = tid; i < D * 64 + n_h * 64; i += NTHREADS) {
-    // W0t and biases are contiguous in params for n_h layers; smem keeps 4 bias rows
-    sPar[i] = a.params[i];
-  }
+  // ---- one-time setup (all warps)
+  for (int i = tid; i < D * 64 + n_h * 64; i += NTHREADS) sPar[i] = a.params[i];
   for (int i = tid; i < 64 + 1; i += NTHREADS) sWL[i] = a.params[D * 64 + n_h * 64 + i];
-  // indicator tiles: E_n has row n all ones (bf16 1.0 = 0x3F80), others zero; X^T lo tile row D zero
   for (int i = tid; i < (1024 * (D > 0 ? D : 1)) / 4; i += NTHREADS) {
     const int n = i / 256, w = i % 256;  // tile n, 32-bit word w: row = w / 32
-    reinterpret_cast<uint32_t*>(ET)[i] = ((w >> 5) == n) ? 0x3F803F80u : 0u;
+    reinterpret_cast<uint32_t*>(sm + SM::off_E)[i] = ((w >> 5) == n) ? 0x3F803F80u : 0u;
   }
   for (int i = tid; i < 512; i += NTHREADS) {
     const int t = i / 256, w = i % 256;
-    reinterpret_cast<uint32_t*>(XT)[i] = (t == 0 && (w >> 5) == D) ? 0x3F803F80u : 0u;
+    reinterpret_cast<uint32_t*>(sm + SM::off_XT)[i] = (t == 0 && (w >> 5) == D) ? 0x3F803F80u : 0u;
+  }
+  {
+    // resident: every hidden layer's W; otherwise W_1 (later layers are streamed by the issuer)
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+    uint4* dst = reinterpret_cast<uint4*>(sm + SM::off_W);
+    for (int i = tid; i < (WRES ? n_h - 1 : 1) * 2 * TILE_BYTES / 16; i += NTHREADS) dst[i] = src[i];
   }
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int j = 0; j < 4; ++j) mbar_init(&bar_chunk[j], NEPI);
+    mbar_init(bar_d, 1);
+    mbar_init(bar_w, 1);
+    mbar_init(bar_own, 1);
+    mbar_init(bar_wt, 1);
     fence_mbar_init();
+    if (sbase & 1023u) __trap();   // SWIZZLE_128B tiles need the 1024-byte alignment the declaration asks for
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  uint32_t phase = 0;
 
-  const uint32_t sT1 = smem_u32(T1), sT2 = smem_u32(T2), sWT = smem_u32(WT), sXT = smem_u32(XT), sET = smem_u32(ET);
-  constexpr uint32_t ID_FWD = make_idesc(64, 64, 0, 0);   // A K-major, B K-major
-  constexpr uint32_t ID_DG = make_idesc(64, 64, 0, 1);    // A K-major, B MN-major (W viewed as W^T)
-  constexpr uint32_t ID_WG = make_idesc(64, 64, 1, 1);    // A, B MN-major (contraction over points)
-  constexpr uint32_t ID_SM = make_idesc(64, 8, 1, 0);     // A MN-major, B K-major, N = 8
+  // this CTA's contiguous range of tiles
+  const int tile_begin = (int)(((long long)a.num_tiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long long)a.num_tiles * (blockIdx.x + 1)) / gridDim.x);
 
-  double qs[4] = {0.0, 0.0, 0.0, 0.0};
-  double gE = 0.0;
-  float gwl[4][2];   // output-layer weight gradient partials of this thread's columns
-#pragma unroll
-  for (int j = 0; j < 4; ++j) gwl[j][0] = gwl[j][1] = 0.f;
-  float gbl = 0.f;   // output bias gradient partial (program threads)
-  bool first_tile = true;
+  // accumulator address of jet channel c in region r: pair c/2 at columns 64 (c/2), lane half c%2
+  auto d_addr = [&](int r, int c) { return taddr_of(tmem, 16 * (c & 1), COL_R0 + 192 * r + 64 * (c >> 1)); };
+  auto w_addr = [&](int l) { return sWT + (WRES ? (l - 1) * 2 * TILE_BYTES : 0); };
 
-  auto load_W = [&](int l) {   // GEMM layer l (1..n_h-1) -> WT
-    const uint4* src = reinterpret_cast<const uint4*>(a.wimg + (size_t)(l - 1) * 2 * TILE_BYTES);
-    uint4* dst = reinterpret_cast<uint4*>(WT);
-#pragma unroll
-    for (int i = 0; i < (2 * TILE_BYTES / 16) / NTHREADS; ++i) dst[tid + i * NTHREADS] = src[tid + i * NTHREADS];
-  };
-  // accumulator address of jet channel c: pair c/2 at columns 64 (c/2), lane half c%2
-  auto d_addr = [&](int c) { return taddr_of(tmem, 16 * (c & 1), COL_R0 + 64 * (c >> 1)); };
-  // all threads: make generic smem writes visible to the tensor core, then hand over to the issuer
-  auto sync_to_mma = [&]() {
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-  };
-  auto wait_mma = [&]() {
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-  };
-  auto stash_idx = [&](int l, int j, int v) { return (((l * 4 + j) * NWARPS + warp) * NV + v) * 32 + lane; };
-
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-    const long long base = (long long)tile * TP;
-    // ---- points of this tile; x^T operand tile for the first-layer weight gradient
-    for (int i = tid; i < TP * D; i += NTHREADS) {
-      const long long gp = base + i / D;
-      sX[i] = (gp < a.n) ? a.X[gp * D + (i % D)] : 0.f;
-    }
-    __syncthreads();
-    if (do_bwd) {
-      for (int i = tid; i < D * 32; i += NTHREADS) {
-        const int j = i / 32, pp = 2 * (i % 32);   // row j of X^T, points pp, pp+1
-        uint32_t hi, lo;
-        split2(sX[pp * D + j], sX[(pp + 1) * D + j], hi, lo);
-        const uint32_t off = tile_off(j, pp >> 3) + ((pp & 7) << 1);
-        *reinterpret_cast<uint32_t*>(XT + off) = hi;
-        *reinterpret_cast<uint32_t*>(XT + 1024 + off) = lo;
-      }
-    }
-
-    float outacc[2][C];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int c = 0; c < C; ++c) outacc[r][c] = 0.f;
-
-    // ================= forward =================
-    for (int l = 0; l < n_h; ++l) {
-      if (l >= 1) {
-        load_W(l);
-        sync_to_mma();
-        if (warp == 0) {
-          if (lane == 0) {
+  if (warp == NEPI) {
+    // =====================================================================================
+    // MMA issuer
+    // =====================================================================================
+    if (lane == 0) {
+      constexpr uint32_t ID_FWD = make_idesc(64, 64, 0, 0);   // A K-major, B K-major
+      constexpr uint32_t ID_DG = make_idesc(64, 64, 0, 1);    // A K-major, B MN-major (W viewed as W^T)
+      constexpr uint32_t ID_WG = make_idesc(64, 64, 1, 1);    // A, B MN-major (contraction over points)
+      constexpr uint32_t ID_SM = make_idesc(64, 8, 1, 0);     // A MN-major, B K-major, N = 8
+      uint32_t ph_chunk = 0, ph_own = 0, ph_wt = 0;
+      int reg = 0;   // region the next D-producing GEMM writes
+      bool first_tile = true;
+      int cur_w = 1;   // layer whose W sits in the single buffer (non-resident W)
+      // make W_l the resident tile pair: drain my MMAs (they may read the buffer), then one bulk copy
+      auto need_w = [&](int l) {
+        if (WRES || cur_w == l) return;
+        mma_commit(bar_own);
+        mbar_wait(bar_own, ph_own);
+        ph_own ^= 1;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_wt)), "r"(2 * TILE_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWT),
+                     "l"(a.wimg + (size_t)(l - 1) * 2 * TILE_BYTES), "r"(2 * TILE_BYTES), "r"(smem_u32(bar_wt))
+                     : "memory");
+        mbar_wait(bar_wt, ph_wt);
+        ph_wt ^= 1;
+        cur_w = l;
+      };
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        // ---- forward GEMMs of layers 1..n_h-1, K step j as soon as chunk j of A_{l-1} is there
+        for (int l = 1; l < n_h; ++l) {
+          const uint32_t wt = w_addr(l);
+          need_w(l);
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(&bar_chunk[j], ph_chunk);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < C; ++c) {
-              const uint32_t d = d_addr(c);
-              uint32_t acc = 0;
-#pragma unroll 1
-              for (int t = 0; t < 3; ++t) {
-                const uint32_t at = sT1 + (2 * c + (t == 1 ? 1 : 0)) * TILE_BYTES;
-                const uint32_t bt = sWT + (t == 2 ? TILE_BYTES : 0);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  mma_bf16(d, desc_kmajor(at, ks), desc_kmajor(bt, ks), ID_FWD, acc);
-                  acc = 1;
-                }
+            for (int c = 0; c < C; ++c) {
+              const uint32_t d = d_addr(reg, c);
+              const uint32_t ah = sT1 + (2 * c) * TILE_BYTES, al = ah + TILE_BYTES;
+              mma_bf16(d, kdesc(ah, j), kdesc(wt, j), ID_FWD, j > 0 ? 1u : 0u);
+              mma_bf16(d, kdesc(al, j), kdesc(wt, j), ID_FWD, 1u);
+              mma_bf16(d, kdesc(ah, j), kdesc(wt + TILE_BYTES, j), ID_FWD, 1u);
+            }
+          }
+          mma_commit(bar_d);
+          ph_chunk ^= 1;
+          reg ^= 1;
+        }
+        if (!do_bwd) continue;
+        // ---- reverse sweep
+        for (int l = n_h - 1; l >= 1; --l) {
+          const uint32_t wt = w_addr(l);
+          need_w(l);
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(&bar_chunk[j], ph_chunk);
+            tc_fence_after();
+            // dgrad: Ab_{l-1,c} += Zb_{l,c}[:, K step j] W_l[K step j, :]
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const uint32_t d = d_addr(reg, c);
+              const uint32_t zh = sT2 + (2 * c) * TILE_BYTES, zl = zh + TILE_BYTES;
+              mma_bf16(d, kdesc(zh, j), mdesc(wt, j), ID_DG, j > 0 ? 1u : 0u);
+              mma_bf16(d, kdesc(zl, j), mdesc(wt, j), ID_DG, 1u);
+              mma_bf16(d, kdesc(zh, j), mdesc(wt + TILE_BYTES, j), ID_DG, 1u);
+            }
+          }
+          mma_commit(bar_d);
+          ph_chunk ^= 1;
+          reg ^= 1;
+          // wgrad: gW_l += sum_c Zb_{l,c}^T A_{l-1,c}   (K = 64 points)
+          {
+            const int sl = l - 1;
+            const uint32_t d = taddr_of(tmem, 16 * (sl & 1), COL_G + 64 * (sl >> 1));
+            uint32_t acc = first_tile ? 0u : 1u;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const uint32_t zh = sT2 + (2 * c) * TILE_BYTES, zl = zh + TILE_BYTES;
+              const uint32_t ah = sT1 + (2 * c) * TILE_BYTES, al = ah + TILE_BYTES;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_bf16(d, mdesc(zh, ks), mdesc(ah, ks), ID_WG, acc);
+                acc = 1u;
+                mma_bf16(d, mdesc(zl, ks), mdesc(ah, ks), ID_WG, 1u);
+                mma_bf16(d, mdesc(zh, ks), mdesc(al, ks), ID_WG, 1u);
               }
             }
-            mma_commit(bar);
+            // bias: gb_l += Zb_{l,0}^T 1
+            const uint32_t db = taddr_of(tmem, 16, COL_SMALL + 8 * l);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_bf16(db, mdesc(sT2, ks), kdesc(sET, ks), ID_SM, (first_tile && ks == 0) ? 0u : 1u);
+              mma_bf16(db, mdesc(sT2 + TILE_BYTES, ks), kdesc(sET, ks), ID_SM, 1u);
+            }
           }
-          __syncwarp();
+          mma_commit(bar_w);
         }
-        wait_mma();
-      }
-      const bool last = (l == n_h - 1);
+        // ---- first layer: [gW0 | gb0] += Zb_{0,0}^T [x | 1] + sum_i Zb_{0,i}^T e_i
+        {
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int u0 = 16 * j + 8 * h + cq;   // this thread's columns u0, u0+1
-        float z[C][4];                        // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]
-        if (l == 0) {
+          for (int j = 0; j < 4; ++j) mbar_wait(&bar_chunk[j], ph_chunk);
+          tc_fence_after();
+          ph_chunk ^= 1;
+          const uint32_t d = taddr_of(tmem, 16, COL_SMALL);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int row = (e < 2) ? r0 : r1, u = u0 + (e & 1);
-            float v = sB[u];
-#pragma unroll
-            for (int jd = 0; jd < D; ++jd) v = fmaf(sW0t[jd * 64 + u], sX[row * D + jd], v);
-            z[0][e] = v;
-#pragma unroll
-            for (int i = 0; i < ND; ++i) z[1 + i][e] = sW0t[i * 64 + u];
-            if constexpr (LAP) z[1 + ND][e] = 0.f;
+          for (int ks = 0; ks < 4; ++ks) {
+            mma_bf16(d, mdesc(sT2, ks), kdesc(sXT, ks), ID_SM, (first_tile && ks == 0) ? 0u : 1u);
+            mma_bf16(d, mdesc(sT2 + TILE_BYTES, ks), kdesc(sXT, ks), ID_SM, 1u);
+            mma_bf16(d, mdesc(sT2, ks), kdesc(sXT + 1024, ks), ID_SM, 1u);
           }
-        } else {
-#pragma unroll
-          for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(c) + ((32 * q) << 16) + 16 * j + 8 * h, z[c]);
-          tmem_ld_wait();
-          const float b0v = sB[l * 64 + u0], b1v = sB[l * 64 + u0 + 1];
-          z[0][0] += b0v; z[0][1] += b1v; z[0][2] += b0v; z[0][3] += b1v;
-        }
-        float av[C][4], sv0[4], sv1[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          act_eval(act, z[0][e], sv0[e], sv1[e]);
-          float s0, s1, s2, s3;
-          act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
-          av[0][e] = s0;
-          float S = 0.f;
 #pragma unroll
           for (int i = 0; i < ND; ++i) {
-            av[1 + i][e] = s1 * z[1 + i][e];
-            S = fmaf(z[1 + i][e], z[1 + i][e], S);
-          }
-          if constexpr (LAP) av[1 + ND][e] = fmaf(s1, z[1 + ND][e], s2 * S);
-        }
-        if (do_bwd) {
-          stash[stash_idx(l, j, 0)] = make_float4(sv0[0], sv0[1], sv0[2], sv0[3]);
-          stash[stash_idx(l, j, 1)] = make_float4(sv1[0], sv1[1], sv1[2], sv1[3]);
-          if (l >= 1) {
 #pragma unroll
-            for (int c = 1; c < C; ++c) stash[stash_idx(l, j, 1 + c)] = make_float4(z[c][0], z[c][1], z[c][2], z[c][3]);
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_bf16(d, mdesc(sT2 + (2 * (1 + i)) * TILE_BYTES, ks), kdesc(sET + 1024 * i, ks), ID_SM, 1u);
+              mma_bf16(d, mdesc(sT2 + (2 * (1 + i) + 1) * TILE_BYTES, ks), kdesc(sET + 1024 * i, ks), ID_SM, 1u);
+            }
           }
+          mma_commit(bar_w);
         }
-        if (!last) {
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            store_pair(T1, c, r0, u0, av[c][0], av[c][1]);
-            store_pair(T1, c, r1, u0, av[c][2], av[c][3]);
-          }
-        } else {
-          const float w0v = sWL[u0], w1v = sWL[u0 + 1];
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            outacc[0][c] = fmaf(w0v, av[c][0], fmaf(w1v, av[c][1], outacc[0][c]));
-            outacc[1][c] = fmaf(w0v, av[c][2], fmaf(w1v, av[c][3], outacc[1][c]));
-          }
-        }
+        first_tile = false;
       }
     }
+    __syncwarp();
+  } else {
+    // =====================================================================================
+    // epilogue warps
+    // =====================================================================================
+    const int q = warp & 3, h = warp >> 2;
+    const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;   // this thread's two points (tile rows)
+    const int cq = 2 * (lane & 3);                      // column offset inside an 8-column block
+    // stmatrix row address of this thread: matrix i = lane/8 (hi r0-rows, hi r1-rows, lo r0-rows, lo r1-rows)
+    const int sm_row = 16 * q + 8 * ((lane >> 3) & 1) + (lane & 7);
+    const uint32_t sm_base = (uint32_t)((lane >> 4) * TILE_BYTES) + ((sm_row >> 3) << 10) + ((sm_row & 7) << 7);
+    const int sm_r7 = sm_row & 7;
+    float* part = a.partial + (long long)blockIdx.x * a.PP;
+    float4* stash = a.stash + (long long)blockIdx.x * a.stash_f4 + warp * (NV * 32) + lane;
+    uint32_t ph_d = 0, ph_w = 0;
+    int reg = 0;   // region the next D-consuming step reads
+    bool w_pending = false;   // a bar_w commit has been issued that nobody waited for yet
 
-    // ================= output layer + envelope + residual program =================
+    double qs[4] = {0.0, 0.0, 0.0, 0.0};
+    double gE = 0.0;
+    float gwl[4][2];   // output-layer weight gradient partials of this thread's columns
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int j = 0; j < 4; ++j) gwl[j][0] = gwl[j][1] = 0.f;
+    float gbl = 0.f;   // output bias gradient partial (program threads)
+
+    // write 4 values (2 rows x 2 adjacent units) of every channel of chunk j into an operand set
+    auto store_chunk = [&](uint32_t set, int j, const float (&v)[C][4]) {
+      const uint32_t addr = set + sm_base + ((((2 * j + h) ^ sm_r7) & 7) << 4);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        float v = outacc[r][c];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        outacc[r][c] = v;
+        uint32_t h0, l0, h1, l1;
+        split2(v[c][0], v[c][1], h0, l0);
+        split2(v[c][2], v[c][3], h1, l1);
+        stsm_x4(addr + c * 2 * TILE_BYTES, h0, h1, l0, l1);
       }
-    if ((lane & 3) == 0) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        sRed[(h * 64 + r0) * C + c] = outacc[0][c];
-        sRed[(h * 64 + r1) * C + c] = outacc[1][c];
-      }
-    }
-    __syncthreads();
-    if (tid < TP) {
-      const long long gp = base + tid;
-      float nj[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) nj[c] = sRed[tid * C + c] + sRed[(64 + tid) * C + c];
-      nj[0] += sWL[64];
-      if (gp < a.n) {
-        program_point_lap<D, ORDER>(a, sX + tid * D, gp, nj, qs, gE);
-        gbl += nj[0];
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; ++c) nj[c] = 0.f;
-      }
-#pragma unroll
-      for (int c = 0; c < C; ++c) sNb[tid * C + c] = nj[c];
-    }
-    __syncthreads();
-    if (!do_bwd) continue;
+    };
+    auto chunk_done = [&](int j) {
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_chunk[j]);
+    };
+    auto stash_at = [&](int l, int j, int v) { return stash + ((l * 4 + j) * NEPI * NV + v) * 32; };
 
-    // ================= reverse sweep =================
-    for (int l = n_h - 1; l >= 0; --l) {
-      const bool top = (l == n_h - 1);
-      if (l >= 1) load_W(l);   // the previous MMAs reading WT have completed (wait_mma)
-#pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
-        const int u0 = 16 * j + 8 * h + cq;
-        float ab[C][4];
-        if (top) {
-          const float w0v = sWL[u0], w1v = sWL[u0 + 1];
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float n0 = sNb[r0 * C + c], n1 = sNb[r1 * C + c];
-            ab[c][0] = w0v * n0; ab[c][1] = w1v * n0; ab[c][2] = w0v * n1; ab[c][3] = w1v * n1;
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(c) + ((32 * q) << 16) + 16 * j + 8 * h, ab[c]);
-          tmem_ld_wait();
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const long long base = (long long)tile * TP;
+      // every MMA of the previous tile has completed before X^T / the operand sets are rewritten
+      if (w_pending) {
+        mbar_wait(bar_w, ph_w);
+        ph_w ^= 1;
+        w_pending = false;
+      }
+      named_sync(1, NEPI * 32);   // everyone is done with sX / sNb / sRed of the previous tile
+      for (int i = tid; i < TP * D; i += NEPI * 32) {
+        const long long gp = base + i / D;
+        sX[i] = (gp < a.n) ? a.X[gp * D + (i % D)] : 0.f;
+      }
+      named_sync(1, NEPI * 32);
+      if (do_bwd) {
+        for (int i = tid; i < D * 32; i += NEPI * 32) {
+          const int j = i / 32, pp = 2 * (i % 32);   // row j of X^T, points pp, pp+1
+          uint32_t hi, lo;
+          split2(sX[pp * D + j], sX[(pp + 1) * D + j], hi, lo);
+          const uint32_t off = tile_off(j, pp >> 3) + ((pp & 7) << 1);
+          sts32(sXT + off, hi);
+          sts32(sXT + 1024 + off, lo);
         }
-        // stash of this layer: activation values and pre-activation jets
-        const float4 q0 = stash[stash_idx(l, j, 0)], q1 = stash[stash_idx(l, j, 1)];
-        const float sv0[4] = {q0.x, q0.y, q0.z, q0.w}, sv1[4] = {q1.x, q1.y, q1.z, q1.w};
-        float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
+      }
+
+      float outacc[2][C];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) outacc[r][c] = 0.f;
+
+      // ================= forward =================
+      for (int l = 0; l < n_h; ++l) {
+        const bool last = (l == n_h - 1);
         if (l >= 1) {
+          mbar_wait(bar_d, ph_d);
+          ph_d ^= 1;
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int u0 = 16 * j + 8 * h + cq;   // this thread's columns u0, u0+1
+          float z[C][4];                        // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]
+          if (l == 0) {
 #pragma unroll
-          for (int c = 1; c < C; ++c) {
-            const float4 t = stash[stash_idx(l, j, 1 + c)];
-            zj[c][0] = t.x; zj[c][1] = t.y; zj[c][2] = t.z; zj[c][3] = t.w;
+            for (int e = 0; e < 4; ++e) {
+              const int row = (e < 2) ? r0 : r1, u = u0 + (e & 1);
+              float v = sB[u];
+#pragma unroll
+              for (int jd = 0; jd < D; ++jd) v = fmaf(sW0t[jd * 64 + u], sX[row * D + jd], v);
+              z[0][e] = v;
+#pragma unroll
+              for (int i = 0; i < ND; ++i) z[1 + i][e] = sW0t[i * 64 + u];
+              if constexpr (LAP) z[1 + ND][e] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(reg, c) + ((32 * q) << 16) + 16 * j + 8 * h, z[c]);
+            tmem_ld_wait();
+            const float b0v = sB[l * 64 + u0], b1v = sB[l * 64 + u0 + 1];
+            z[0][0] += b0v; z[0][1] += b1v; z[0][2] += b0v; z[0][3] += b1v;
           }
-        } else {
+          float av[C][4], sv0[4], sv1[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int u = u0 + (e & 1);
+            act_eval(act, z[0][e], sv0[e], sv1[e]);
+            float s0, s1, s2, s3;
+            act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
+            av[0][e] = s0;
+            float S = 0.f;
 #pragma unroll
-            for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[i * 64 + u];
-            if constexpr (LAP) zj[1 + ND][e] = 0.f;
+            for (int i = 0; i < ND; ++i) {
+              av[1 + i][e] = s1 * z[1 + i][e];
+              S = fmaf(z[1 + i][e], z[1 + i][e], S);
+            }
+            if constexpr (LAP) av[1 + ND][e] = fmaf(s1, z[1 + ND][e], s2 * S);
+          }
+          if (do_bwd) {
+            __stcg(stash_at(l, j, 0), make_float4(sv0[0], sv0[1], sv0[2], sv0[3]));
+            __stcg(stash_at(l, j, 1), make_float4(sv1[0], sv1[1], sv1[2], sv1[3]));
+            if (l >= 1) {
+#pragma unroll
+              for (int c = 1; c < C; ++c) __stcg(stash_at(l, j, 1 + c), make_float4(z[c][0], z[c][1], z[c][2], z[c][3]));
+            }
+          }
+          if (!last) {
+            store_chunk(sT1, j, av);
+            chunk_done(j);
+          } else {
+            const float w0v = sWL[u0], w1v = sWL[u0 + 1];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              outacc[0][c] = fmaf(w0v, av[c][0], fmaf(w1v, av[c][1], outacc[0][c]));
+              outacc[1][c] = fmaf(w0v, av[c][2], fmaf(w1v, av[c][3], outacc[1][c]));
+            }
           }
         }
-        float zb[C][4];
+        if (l >= 1) reg ^= 1;
+      }
+
+      // ================= output layer + envelope + residual program =================
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float s0, s1, s2, s3;
-          act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
-          float t0 = s1 * ab[0][e];
-          float abL = 0.f;
-          if constexpr (LAP) abL = ab[1 + ND][e];
-          float S = 0.f;
-#pragma unroll
-          for (int i = 0; i < ND; ++i) {
-            const float zi = zj[1 + i][e];
-            t0 = fmaf(s2 * zi, ab[1 + i][e], t0);
-            S = fmaf(zi, zi, S);
-            float ti = s1 * ab[1 + i][e];
-            if constexpr (LAP) ti = fmaf(2.f * s2 * zi, abL, ti);
-            zb[1 + i][e] = ti;
-          }
-          if constexpr (LAP) {
-            t0 = fmaf(fmaf(s2, zj[1 + ND][e], s3 * S), abL, t0);
-            zb[1 + ND][e] = s1 * abL;
-          }
-          zb[0][e] = t0;
-          if (top) {
-            // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
-            const int r = (e < 2) ? r0 : r1;
-            float g = sNb[r * C] * s0;
-#pragma unroll
-            for (int i = 0; i < ND; ++i) g = fmaf(sNb[r * C + 1 + i], s1 * zj[1 + i][e], g);
-            if constexpr (LAP) g = fmaf(sNb[r * C + 1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
-            gwl[j][e & 1] += g;
-          }
-        }
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          store_pair(T2, c, r0, u0, zb[c][0], zb[c][1]);
-          store_pair(T2, c, r1, u0, zb[c][2], zb[c][3]);
+          float v = outacc[r][c];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          outacc[r][c] = v;
         }
-        if (l >= 1) {
-          // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
-          const float4 p0 = stash[stash_idx(l - 1, j, 0)], p1 = stash[stash_idx(l - 1, j, 1)];
-          const float pv0[4] = {p0.x, p0.y, p0.z, p0.w}, pv1[4] = {p1.x, p1.y, p1.z, p1.w};
-          float zp[C][4];
-          if (l - 1 >= 1) {
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          sRed[(h * 64 + r0) * C + c] = outacc[0][c];
+          sRed[(h * 64 + r1) * C + c] = outacc[1][c];
+        }
+      }
+      named_sync(1, NEPI * 32);
+      if (tid < TP) {
+        const long long gp = base + tid;
+        float nj[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) nj[c] = sRed[tid * C + c] + sRed[(64 + tid) * C + c];
+        nj[0] += sWL[64];
+        if (gp < a.n) {
+          program_point_lap<D, ORDER>(a, sX + tid * D, gp, nj, qs, gE);
+          gbl += nj[0];
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) nj[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) sNb[tid * C + c] = nj[c];
+      }
+      named_sync(1, NEPI * 32);
+      if (!do_bwd) continue;
+
+      // ================= reverse sweep =================
+      for (int l = n_h - 1; l >= 0; --l) {
+        const bool top = (l == n_h - 1);
+        if (!top) {
+          mbar_wait(bar_d, ph_d);   // Ab_l is complete
+          ph_d ^= 1;
+          tc_fence_after();
+        }
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int u0 = 16 * j + 8 * h + cq;
+          float ab[C][4];
+          if (top) {
+            const float w0v = sWL[u0], w1v = sWL[u0 + 1];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const float n0 = sNb[r0 * C + c], n1 = sNb[r1 * C + c];
+              ab[c][0] = w0v * n0; ab[c][1] = w1v * n0; ab[c][2] = w0v * n1; ab[c][3] = w1v * n1;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(reg, c) + ((32 * q) << 16) + 16 * j + 8 * h, ab[c]);
+            tmem_ld_wait();
+          }
+          // stash of this layer: activation values and pre-activation jets
+          const float4 q0 = __ldcg(stash_at(l, j, 0)), q1 = __ldcg(stash_at(l, j, 1));
+          const float sv0[4] = {q0.x, q0.y, q0.z, q0.w}, sv1[4] = {q1.x, q1.y, q1.z, q1.w};
+          float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
+          if (l >= 1) {
 #pragma unroll
             for (int c = 1; c < C; ++c) {
-              const float4 t = stash[stash_idx(l - 1, j, 1 + c)];
-              zp[c][0] = t.x; zp[c][1] = t.y; zp[c][2] = t.z; zp[c][3] = t.w;
+              const float4 t = __ldcg(stash_at(l, j, 1 + c));
+              zj[c][0] = t.x; zj[c][1] = t.y; zj[c][2] = t.z; zj[c][3] = t.w;
             }
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int u = u0 + (e & 1);
 #pragma unroll
-              for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
-              if constexpr (LAP) zp[1 + ND][e] = 0.f;
+              for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[i * 64 + u];
+              if constexpr (LAP) zj[1 + ND][e] = 0.f;
             }
           }
-          float ap[C][4];
+          float zb[C][4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float s0, s1, s2, s3;
-            act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
-            ap[0][e] = s0;
+            act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
+            float t0 = s1 * ab[0][e];
+            float abL = 0.f;
+            if constexpr (LAP) abL = ab[1 + ND][e];
             float S = 0.f;
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
-              ap[1 + i][e] = s1 * zp[1 + i][e];
-              S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
+              const float zi = zj[1 + i][e];
+              t0 = fmaf(s2 * zi, ab[1 + i][e], t0);
+              S = fmaf(zi, zi, S);
+              float ti = s1 * ab[1 + i][e];
+              if constexpr (LAP) ti = fmaf(2.f * s2 * zi, abL, ti);
+              zb[1 + i][e] = ti;
             }
-            if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
-          }
+            if constexpr (LAP) {
+              t0 = fmaf(fmaf(s2, zj[1 + ND][e], s3 * S), abL, t0);
+              zb[1 + ND][e] = s1 * abL;
+            }
+            zb[0][e] = t0;
+            if (top) {
+              // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
+              const int r = (e < 2) ? r0 : r1;
+              float g = sNb[r * C] * s0;
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            store_pair(T1, c, r0, u0, ap[c][0], ap[c][1]);
-            store_pair(T1, c, r1, u0, ap[c][2], ap[c][3]);
+              for (int i = 0; i < ND; ++i) g = fmaf(sNb[r * C + 1 + i], s1 * zj[1 + i][e], g);
+              if constexpr (LAP) g = fmaf(sNb[r * C + 1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
+              gwl[j][e & 1] += g;
+            }
           }
-        }
-      }
-      sync_to_mma();
-      if (warp == 0) {
-        if (lane == 0) {
-          tc_fence_after();
+          if (j == 0 && w_pending) {
+            // the previous layer's wgrad still reads both operand sets: wait for it before the first store
+            mbar_wait(bar_w, ph_w);
+            ph_w ^= 1;
+            w_pending = false;
+          }
+          store_chunk(sT2, j, zb);
           if (l >= 1) {
-            // dgrad: Ab_{l-1,c} = Zb_{l,c} W_l
-#pragma unroll 1
-            for (int c = 0; c < C; ++c) {
-              const uint32_t d = d_addr(c);
-              uint32_t acc = 0;
-#pragma unroll 1
-              for (int t = 0; t < 3; ++t) {
-                const uint32_t at = sT2 + (2 * c + (t == 1 ? 1 : 0)) * TILE_BYTES;
-                const uint32_t bt = sWT + (t == 2 ? TILE_BYTES : 0);
+            // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
+            const float4 p0 = __ldcg(stash_at(l - 1, j, 0)), p1 = __ldcg(stash_at(l - 1, j, 1));
+            const float pv0[4] = {p0.x, p0.y, p0.z, p0.w}, pv1[4] = {p1.x, p1.y, p1.z, p1.w};
+            float zp[C][4];
+            if (l - 1 >= 1) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  mma_bf16(d, desc_kmajor(at, ks), desc_mnmajor(bt, ks), ID_DG, acc);
-                  acc = 1;
-                }
+              for (int c = 1; c < C; ++c) {
+                const float4 t = __ldcg(stash_at(l - 1, j, 1 + c));
+                zp[c][0] = t.x; zp[c][1] = t.y; zp[c][2] = t.z; zp[c][3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int u = u0 + (e & 1);
+#pragma unroll
+                for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
+                if constexpr (LAP) zp[1 + ND][e] = 0.f;
               }
             }
-            // wgrad: gW_l += sum_c Zb_{l,c}^T A_{l-1,c}
-            {
-              const int sl = l - 1;
-              const uint32_t d = taddr_of(tmem, 16 * (sl & 1), COL_G + 64 * (sl >> 1));
-              uint32_t acc = first_tile ? 0u : 1u;
-#pragma unroll 1
-              for (int c = 0; c < C; ++c) {
-#pragma unroll 1
-                for (int t = 0; t < 3; ++t) {
-                  const uint32_t at = sT2 + (2 * c + (t == 1 ? 1 : 0)) * TILE_BYTES;
-                  const uint32_t bt = sT1 + (2 * c + (t == 2 ? 1 : 0)) * TILE_BYTES;
+            float ap[C][4];
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    mma_bf16(d, desc_mnmajor(at, ks), desc_mnmajor(bt, ks), ID_WG, acc);
-                    acc = 1;
-                  }
-                }
-              }
-            }
-            // bias: gb_l += Zb_{l,0}^T 1
-            {
-              const uint32_t d = taddr_of(tmem, 16, COL_SMALL + 8 * l);
-              uint32_t acc = first_tile ? 0u : 1u;
-#pragma unroll 1
-              for (int t = 0; t < 2; ++t) {
+            for (int e = 0; e < 4; ++e) {
+              float s0, s1, s2, s3;
+              act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
+              ap[0][e] = s0;
+              float S = 0.f;
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  mma_bf16(d, desc_mnmajor(sT2 + t * TILE_BYTES, ks), desc_kmajor(sET, ks), ID_SM, acc);
-                  acc = 1;
-                }
+              for (int i = 0; i < ND; ++i) {
+                ap[1 + i][e] = s1 * zp[1 + i][e];
+                S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
               }
+              if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
             }
-          } else {
-            // first layer: [gW0 | gb0] += Zb_{0,0}^T [x | 1] + sum_i Zb_{0,i}^T e_i
-            const uint32_t d = taddr_of(tmem, 16, COL_SMALL);
-            uint32_t acc = first_tile ? 0u : 1u;
-#pragma unroll 1
-            for (int t = 0; t < 3; ++t) {
-              const uint32_t at = sT2 + (t == 1 ? 1 : 0) * TILE_BYTES;
-              const uint32_t bt = sXT + (t == 2 ? 1024 : 0);
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                mma_bf16(d, desc_mnmajor(at, ks), desc_kmajor(bt, ks), ID_SM, acc);
-                acc = 1;
-              }
-            }
-#pragma unroll 1
-            for (int i = 0; i < ND; ++i) {
-#pragma unroll 1
-              for (int t = 0; t < 2; ++t) {
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  mma_bf16(d, desc_mnmajor(sT2 + (2 * (1 + i) + t) * TILE_BYTES, ks), desc_kmajor(sET + 1024 * i, ks), ID_SM, 1u);
-              }
-            }
+            store_chunk(sT1, j, ap);
           }
-          mma_commit(bar);
+          chunk_done(j);
         }
-        __syncwarp();
+        if (!top) reg ^= 1;
+        w_pending = true;   // the issuer commits bar_w after this step's wgrad / first-layer MMAs
       }
-      wait_mma();
     }
-    first_tile = false;
-  }
 
-  // ================= per-CTA results =================
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (do_bwd) {
-    // hidden GEMM layers: gW_l at slot l-1, rows o = 16 q + lane/4 (+8), columns i
-    for (int l = 1; l < n_h; ++l) {
-      const int sl = l - 1;
-      float* gW = part + a.off_gW + (long long)sl * ((long long)HP * HP + HP);
-      const uint32_t d = taddr_of(tmem, 32 * q + 16 * (sl & 1), COL_G + 64 * (sl >> 1));
+    // ================= per-CTA results =================
+    if (w_pending) {
+      mbar_wait(bar_w, ph_w);
+      ph_w ^= 1;
+    }
+    tc_fence_after();
+    if (do_bwd) {
+      // hidden GEMM layers: gW_l at slot l-1, rows o = 16 q + lane/4 (+8), columns i
+      for (int l = 1; l < n_h; ++l) {
+        const int sl = l - 1;
+        float* gW = part + a.off_gW + (long long)sl * ((long long)HP * HP + HP);
+        const uint32_t d = taddr_of(tmem, 32 * q + 16 * (sl & 1), COL_G + 64 * (sl >> 1));
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        float v[4];
-        tmem_ld_16x256b(d + 32 * h + 8 * b, v);
-        tmem_ld_wait();
-        const int i0 = 32 * h + 8 * b + cq;
-        *reinterpret_cast<float2*>(gW + r0 * HP + i0) = make_float2(v[0], v[1]);
-        *reinterpret_cast<float2*>(gW + r1 * HP + i0) = make_float2(v[2], v[3]);
+        for (int b = 0; b < 4; ++b) {
+          float v[4];
+          tmem_ld_16x256b(d + 32 * h + 8 * b, v);
+          tmem_ld_wait();
+          const int i0 = 32 * h + 8 * b + cq;
+          *reinterpret_cast<float2*>(gW + r0 * HP + i0) = make_float2(v[0], v[1]);
+          *reinterpret_cast<float2*>(gW + r1 * HP + i0) = make_float2(v[2], v[3]);
+        }
+        if (h == 0) {
+          float v[4];
+          tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL + 8 * l), v);
+          tmem_ld_wait();
+          if ((lane & 3) == 0) {
+            gW[HP * HP + r0] = v[0];
+            gW[HP * HP + r1] = v[2];
+          }
+        }
       }
       if (h == 0) {
         float v[4];
-        tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL + 8 * l), v);
+        tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL), v);
         tmem_ld_wait();
-        if ((lane & 3) == 0) {
-          gW[HP * HP + r0] = v[0];
-          gW[HP * HP + r1] = v[2];
+        // columns cq, cq+1 of [gW0 (D cols) | gb0]
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = cq + (e & 1), o = (e < 2) ? r0 : r1;
+          if (col < D) part[a.off_gW0 + o * D + col] = v[e];
+          else if (col == D) part[a.off_gb0 + o] = v[e];
         }
       }
-    }
-    if (h == 0) {
-      float v[4];
-      tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL), v);
-      tmem_ld_wait();
-      // columns cq, cq+1 of [gW0 (D cols) | gb0]
+      // output layer: reduce the per-thread column partials over the 8 row groups of the warp ...
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = cq + (e & 1), o = (e < 2) ? r0 : r1;
-        if (col < D) part[a.off_gW0 + o * D + col] = v[e];
-        else if (col == D) part[a.off_gb0 + o] = v[e];
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float v = gwl[j][k];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          gwl[j][k] = v;
+        }
+      named_sync(1, NEPI * 32);
+      float* sRedW = sRed;   // [4 quarters][64 columns]
+      if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sRedW[q * 64 + 16 * j + 8 * h + cq] = gwl[j][0];
+          sRedW[q * 64 + 16 * j + 8 * h + cq + 1] = gwl[j][1];
+        }
+      }
+      named_sync(1, NEPI * 32);
+      // ... then over the four quarters in fixed order
+      if (tid < 64) part[a.off_gwL + tid] = (sRedW[tid] + sRedW[64 + tid]) + (sRedW[128 + tid] + sRedW[192 + tid]);
+      named_sync(1, NEPI * 32);
+      if (tid < 64) sRed[tid] = gbl;
+      named_sync(1, NEPI * 32);
+      if (tid == 0) {
+        float v = 0.f;
+        for (int i = 0; i < 64; ++i) v += sRed[i];
+        part[a.off_gbL] = v;
       }
     }
-    // output layer: reduce the per-thread column partials over the 8 row groups of the warp ...
+    named_sync(1, NEPI * 32);
+    {
+      double* dred = reinterpret_cast<double*>(sm + SM::off_T1);   // 64 x 5 doubles
+      if (tid < TP) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        float v = gwl[j][k];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        gwl[j][k] = v;
+        for (int k = 0; k < 4; ++k) dred[tid * 5 + k] = qs[k];
+        dred[tid * 5 + 4] = gE;
       }
-    float* sRedW = sRed;   // [4 quarters][64 columns]
-    if (lane < 4) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        sRedW[q * 64 + 16 * j + 8 * h + cq] = gwl[j][0];
-        sRedW[q * 64 + 16 * j + 8 * h + cq + 1] = gwl[j][1];
+      named_sync(1, NEPI * 32);
+      if (tid < 5) {
+        double v = 0.0;
+        for (int pp = 0; pp < TP; ++pp) v += dred[pp * 5 + tid];
+        a.psums[(long long)blockIdx.x * 8 + tid] = v;
       }
-    }
-    __syncthreads();
-    // ... then over the four quarters in fixed order
-    if (tid < 64) part[a.off_gwL + tid] = (sRedW[tid] + sRedW[64 + tid]) + (sRedW[128 + tid] + sRedW[192 + tid]);
-    __syncthreads();
-    float* sRedB = sRed;
-    if (tid < 64) sRedB[tid] = gbl;
-    __syncthreads();
-    if (tid == 0) {
-      float v = 0.f;
-      for (int i = 0; i < 64; ++i) v += sRedB[i];
-      part[a.off_gbL] = v;
-    }
-    __syncthreads();
-  }
-  {
-    double* dred = reinterpret_cast<double*>(T1);   // 64 x 5 doubles
-    if (tid < TP) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) dred[tid * 5 + k] = qs[k];
-      dred[tid * 5 + 4] = gE;
-    }
-    __syncthreads();
-    if (tid < 5) {
-      double v = 0.0;
-      for (int pp = 0; pp < TP; ++pp) v += dred[pp * 5 + tid];
-      a.psums[(long long)blockIdx.x * 8 + tid] = v;
     }
   }
   tc_fence_before();
@@ -808,7 +883,7 @@ static cudaError_t launch_one(const TcPlan& p, const TcArgs& a, cudaStream_t st)
   if constexpr (C > MAXC) {
     return cudaErrorInvalidValue;
   } else {
-    const int smem = SmemMap<D, C>::total + 1024;
+    const int smem = SmemMap<D, C>::total;
     cudaError_t err = cudaFuncSetAttribute(tc_kernel<D, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
     tc_kernel<D, ORDER><<<p.grid, NTHREADS, smem, st>>>(a);
@@ -889,7 +964,7 @@ static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl) {
   p.off_gbL = p.off_gwL + HP;
   p.PP = rup(p.off_gbL + 1, 4);
   p.n_params = (long long)p.H * p.D + p.H + (long long)(p.n_h - 1) * ((long long)p.H * p.H + p.H) + p.H + 1;
-  p.stash_f4 = (long long)p.n_h * 4 * NWARPS * p.NV * 32;
+  p.stash_f4 = (long long)p.n_h * 4 * NEPI * p.NV * 32;
   p.ws_params = (size_t)rup((p.D * 64 + p.n_h * 64 + 64 + 1) * 4, 256);
   p.ws_wimg = (size_t)(p.n_h - 1) * 2 * TILE_BYTES;
   p.ws_partial = (size_t)rup((long long)p.sms * p.PP * 4, 256);
