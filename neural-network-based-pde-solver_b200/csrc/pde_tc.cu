@@ -35,7 +35,7 @@ namespace tc {
 constexpr int TP = 64;        // points per tile = UMMA M
 constexpr int HP = 64;        // padded hidden width = UMMA N / K
 constexpr int NEPI = 8;       // epilogue warps: quarter q = w % 4 (16 points), column half h = w / 4
-constexpr int NTHREADS = (NEPI + 1) * 32;   // + one MMA-issuer warp
+constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp issues the MMAs (rest idle, registers donated)
 constexpr int MAXC = 6;       // jet channels the TMEM / smem budget covers
 constexpr int COL_R0 = 0;     // TMEM columns: activation / adjoint accumulators (3 interleaved pairs)
 constexpr int COL_G = 384;    // gW accumulators: slot s at column COL_G + 64 (s / 2), lane half s % 2
@@ -70,9 +70,33 @@ __device__ __forceinline__ void act_from_stash(int act, float v0, float v1, floa
     s0 = v0; s1 = v1; s2 = -2.f * v0 * v1; s3 = -2.f * v1 * (1.f - 3.f * v0 * v0);
   }
 }
+// sin and cos to ~1 ulp for |z| < 2^15 (three-term Cody-Waite reduction by pi/2, minimax
+// polynomials on [-pi/4, pi/4]); larger arguments take the library path
+__device__ __forceinline__ void sincos_cw(float z, float& s, float& c) {
+  if (fabsf(z) > 32768.f) {
+    sincosf(z, &s, &c);
+    return;
+  }
+  const float kf = rintf(z * 0.636619772f);
+  const int k = __float2int_rn(kf);
+  float r = fmaf(kf, -1.57079601e+00f, z);
+  r = fmaf(kf, -3.13916473e-07f, r);
+  r = fmaf(kf, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+  sp = fmaf(sp, r2, -1.66666546e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+  cp = fmaf(cp, r2, 4.16666457e-2f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.0f);
+  const float a = (k & 1) ? cp : sp, b = (k & 1) ? sp : cp;
+  s = (k & 2) ? -a : a;
+  c = ((k + 1) & 2) ? -b : b;
+}
 __device__ __forceinline__ void act_eval(int act, float z, float& v0, float& v1) {
   if (act == 0) {
-    sincosf(z, &v0, &v1);
+    sincos_cw(z, v0, v1);
   } else {
     v0 = tanhf(z); v1 = 1.f - v0 * v0;
   }
@@ -206,11 +230,37 @@ __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1,
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// UMMA descriptors as "constant high part + 14-bit start address": K-major / MN-major Tile64 views
-constexpr uint64_t DESC_K = (static_cast<uint64_t>(16 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-constexpr uint64_t DESC_MN = (static_cast<uint64_t>(8192 >> 4) << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-__device__ __forceinline__ uint64_t kdesc(uint32_t saddr, int ks) { return DESC_K | static_cast<uint64_t>((saddr >> 4) + 2 * ks); }
-__device__ __forceinline__ uint64_t mdesc(uint32_t saddr, int ks) { return DESC_MN | static_cast<uint64_t>((saddr >> 4) + 128 * ks); }
+// UMMA descriptors as "constant high word + 14-bit start address (16-byte units) in the low word":
+// K-major / MN-major Tile64 views (LBO 16 / 8192 bytes, SBO 1024 bytes, version 1, SWIZZLE_128B)
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO | version | layout type
+constexpr uint32_t DESC_K_LBO = (16u >> 4) << 16;      // low word, next to the start address
+constexpr uint32_t DESC_MN_LBO = (8192u >> 4) << 16;
+// one tcgen05.mma from 32-bit descriptor words
+__device__ __forceinline__ void mma_k(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ---------------------------------------------------------------- the kernel
 // Warps 0..7: epilogue (quarter q = w % 4 owns points 16q..16q+15, half h = w / 4 owns 8 of the 16
@@ -294,29 +344,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   auto d_addr = [&](int r, int c) { return taddr_of(tmem, 16 * (c & 1), COL_R0 + 192 * r + 64 * (c >> 1)); };
   auto w_addr = [&](int l) { return sWT + (WRES ? (l - 1) * 2 * TILE_BYTES : 0); };
 
-  if (warp == NEPI) {
+  if (warp >= NEPI) {
     // =====================================================================================
-    // MMA issuer
+    // MMA issuer (warp NEPI); its warpgroup hands its registers to the epilogue.  The warp runs
+    // the loops convergently and one elected lane issues, so descriptor arithmetic stays uniform.
     // =====================================================================================
-    if (lane == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (warp == NEPI) {
       constexpr uint32_t ID_FWD = make_idesc(64, 64, 0, 0);   // A K-major, B K-major
       constexpr uint32_t ID_DG = make_idesc(64, 64, 0, 1);    // A K-major, B MN-major (W viewed as W^T)
       constexpr uint32_t ID_WG = make_idesc(64, 64, 1, 1);    // A, B MN-major (contraction over points)
       constexpr uint32_t ID_SM = make_idesc(64, 8, 1, 0);     // A MN-major, B K-major, N = 8
+      constexpr uint32_t TD = TILE_BYTES >> 4;                // one tile in descriptor address units
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+      // low descriptor words (start address in 16-byte units | LBO) of the K-major / MN-major views
+      const uint32_t kT1K = (sT1 >> 4) | DESC_K_LBO, kT1M = (sT1 >> 4) | DESC_MN_LBO;
+      const uint32_t kT2K = (sT2 >> 4) | DESC_K_LBO, kT2M = (sT2 >> 4) | DESC_MN_LBO;
+      const uint32_t kXTK = (sXT >> 4) | DESC_K_LBO, kETK = (sET >> 4) | DESC_K_LBO;
       uint32_t ph_chunk = 0, ph_own = 0, ph_wt = 0;
       int reg = 0;   // region the next D-producing GEMM writes
-      bool first_tile = true;
+      uint32_t acc_g = 0;   // 0 until the gradient accumulators have been initialised by the first tile
       int cur_w = 1;   // layer whose W sits in the single buffer (non-resident W)
       // make W_l the resident tile pair: drain my MMAs (they may read the buffer), then one bulk copy
       auto need_w = [&](int l) {
         if (WRES || cur_w == l) return;
-        mma_commit(bar_own);
+        if (elect_one()) mma_commit(bar_own);
+        __syncwarp();
         mbar_wait(bar_own, ph_own);
         ph_own ^= 1;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_wt)), "r"(2 * TILE_BYTES) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWT),
-                     "l"(a.wimg + (size_t)(l - 1) * 2 * TILE_BYTES), "r"(2 * TILE_BYTES), "r"(smem_u32(bar_wt))
-                     : "memory");
+        if (elect_one()) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_wt)), "r"(2 * TILE_BYTES) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWT),
+                       "l"(a.wimg + (size_t)(l - 1) * 2 * TILE_BYTES), "r"(2 * TILE_BYTES), "r"(smem_u32(bar_wt))
+                       : "memory");
+        }
+        __syncwarp();
         mbar_wait(bar_wt, ph_wt);
         ph_wt ^= 1;
         cur_w = l;
@@ -324,105 +386,116 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         // ---- forward GEMMs of layers 1..n_h-1, K step j as soon as chunk j of A_{l-1} is there
         for (int l = 1; l < n_h; ++l) {
-          const uint32_t wt = w_addr(l);
+          const uint32_t kW = (w_addr(l) >> 4) | DESC_K_LBO;
+          const uint32_t dbase = tm + COL_R0 + 192 * reg;
           need_w(l);
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
             mbar_wait(&bar_chunk[j], ph_chunk);
             tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const uint32_t d = d_addr(reg, c);
-              const uint32_t ah = sT1 + (2 * c) * TILE_BYTES, al = ah + TILE_BYTES;
-              mma_bf16(d, kdesc(ah, j), kdesc(wt, j), ID_FWD, j > 0 ? 1u : 0u);
-              mma_bf16(d, kdesc(al, j), kdesc(wt, j), ID_FWD, 1u);
-              mma_bf16(d, kdesc(ah, j), kdesc(wt + TILE_BYTES, j), ID_FWD, 1u);
+              for (int c = 0; c < C; ++c) {
+                const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
+                const uint32_t ah = kT1K + (2 * c) * TD + 2 * j, al = ah + TD;
+                mma_k(d, ah, DESC_HI, kW + 2 * j, DESC_HI, ID_FWD, j > 0 ? 1u : 0u);
+                mma_k(d, al, DESC_HI, kW + 2 * j, DESC_HI, ID_FWD, 1u);
+                mma_k(d, ah, DESC_HI, kW + TD + 2 * j, DESC_HI, ID_FWD, 1u);
+              }
             }
+            __syncwarp();
           }
-          mma_commit(bar_d);
+          if (elect_one()) mma_commit(bar_d);
+          __syncwarp();
           ph_chunk ^= 1;
           reg ^= 1;
         }
         if (!do_bwd) continue;
         // ---- reverse sweep
         for (int l = n_h - 1; l >= 1; --l) {
-          const uint32_t wt = w_addr(l);
+          const uint32_t kW = (w_addr(l) >> 4) | DESC_MN_LBO;
+          const uint32_t dbase = tm + COL_R0 + 192 * reg;
           need_w(l);
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 4; ++j) {
             mbar_wait(&bar_chunk[j], ph_chunk);
             tc_fence_after();
             // dgrad: Ab_{l-1,c} += Zb_{l,c}[:, K step j] W_l[K step j, :]
+            if (elect_one()) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const uint32_t d = d_addr(reg, c);
-              const uint32_t zh = sT2 + (2 * c) * TILE_BYTES, zl = zh + TILE_BYTES;
-              mma_bf16(d, kdesc(zh, j), mdesc(wt, j), ID_DG, j > 0 ? 1u : 0u);
-              mma_bf16(d, kdesc(zl, j), mdesc(wt, j), ID_DG, 1u);
-              mma_bf16(d, kdesc(zh, j), mdesc(wt + TILE_BYTES, j), ID_DG, 1u);
-            }
-          }
-          mma_commit(bar_d);
-          ph_chunk ^= 1;
-          reg ^= 1;
-          // wgrad: gW_l += sum_c Zb_{l,c}^T A_{l-1,c}   (K = 64 points)
-          {
-            const int sl = l - 1;
-            const uint32_t d = taddr_of(tmem, 16 * (sl & 1), COL_G + 64 * (sl >> 1));
-            uint32_t acc = first_tile ? 0u : 1u;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              const uint32_t zh = sT2 + (2 * c) * TILE_BYTES, zl = zh + TILE_BYTES;
-              const uint32_t ah = sT1 + (2 * c) * TILE_BYTES, al = ah + TILE_BYTES;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                mma_bf16(d, mdesc(zh, ks), mdesc(ah, ks), ID_WG, acc);
-                acc = 1u;
-                mma_bf16(d, mdesc(zl, ks), mdesc(ah, ks), ID_WG, 1u);
-                mma_bf16(d, mdesc(zh, ks), mdesc(al, ks), ID_WG, 1u);
+              for (int c = 0; c < C; ++c) {
+                const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
+                const uint32_t zh = kT2K + (2 * c) * TD + 2 * j, zl = zh + TD;
+                mma_k(d, zh, DESC_HI, kW + 128 * j, DESC_HI, ID_DG, j > 0 ? 1u : 0u);
+                mma_k(d, zl, DESC_HI, kW + 128 * j, DESC_HI, ID_DG, 1u);
+                mma_k(d, zh, DESC_HI, kW + TD + 128 * j, DESC_HI, ID_DG, 1u);
               }
             }
-            // bias: gb_l += Zb_{l,0}^T 1
-            const uint32_t db = taddr_of(tmem, 16, COL_SMALL + 8 * l);
+            __syncwarp();
+          }
+          if (elect_one()) mma_commit(bar_d);
+          __syncwarp();
+          ph_chunk ^= 1;
+          reg ^= 1;
+          // wgrad: gW_l += sum_c Zb_{l,c}^T A_{l-1,c}   (K = 64 points);  bias: gb_l += Zb_{l,0}^T 1
+          if (elect_one()) {
+            const int sl = l - 1;
+            const uint32_t d = tm + ((16 * (sl & 1)) << 16) + COL_G + 64 * (sl >> 1);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t zh = kT2M + (2 * c) * TD + 128 * ks, zl = zh + TD;
+                const uint32_t ah = kT1M + (2 * c) * TD + 128 * ks, al = ah + TD;
+                mma_k(d, zh, DESC_HI, ah, DESC_HI, ID_WG, (c == 0 && ks == 0) ? acc_g : 1u);
+                mma_k(d, zl, DESC_HI, ah, DESC_HI, ID_WG, 1u);
+                mma_k(d, zh, DESC_HI, al, DESC_HI, ID_WG, 1u);
+              }
+            }
+            const uint32_t db = tm + (16u << 16) + COL_SMALL + 8 * l;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              mma_bf16(db, mdesc(sT2, ks), kdesc(sET, ks), ID_SM, (first_tile && ks == 0) ? 0u : 1u);
-              mma_bf16(db, mdesc(sT2 + TILE_BYTES, ks), kdesc(sET, ks), ID_SM, 1u);
+              mma_k(db, kT2M + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? acc_g : 1u);
+              mma_k(db, kT2M + TD + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, 1u);
             }
+            mma_commit(bar_w);
           }
-          mma_commit(bar_w);
+          __syncwarp();
         }
         // ---- first layer: [gW0 | gb0] += Zb_{0,0}^T [x | 1] + sum_i Zb_{0,i}^T e_i
         {
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 4; ++j) mbar_wait(&bar_chunk[j], ph_chunk);
           tc_fence_after();
           ph_chunk ^= 1;
-          const uint32_t d = taddr_of(tmem, 16, COL_SMALL);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            mma_bf16(d, mdesc(sT2, ks), kdesc(sXT, ks), ID_SM, (first_tile && ks == 0) ? 0u : 1u);
-            mma_bf16(d, mdesc(sT2 + TILE_BYTES, ks), kdesc(sXT, ks), ID_SM, 1u);
-            mma_bf16(d, mdesc(sT2, ks), kdesc(sXT + 1024, ks), ID_SM, 1u);
-          }
-#pragma unroll
-          for (int i = 0; i < ND; ++i) {
+          if (elect_one()) {
+            const uint32_t d = tm + (16u << 16) + COL_SMALL;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              mma_bf16(d, mdesc(sT2 + (2 * (1 + i)) * TILE_BYTES, ks), kdesc(sET + 1024 * i, ks), ID_SM, 1u);
-              mma_bf16(d, mdesc(sT2 + (2 * (1 + i) + 1) * TILE_BYTES, ks), kdesc(sET + 1024 * i, ks), ID_SM, 1u);
+              mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? acc_g : 1u);
+              mma_k(d, kT2M + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
+              mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 64 + 2 * ks, DESC_HI, ID_SM, 1u);
             }
+#pragma unroll
+            for (int i = 0; i < ND; ++i) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_k(d, kT2M + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK + 64 * i + 2 * ks, DESC_HI, ID_SM, 1u);
+                mma_k(d, kT2M + (2 * (1 + i) + 1) * TD + 128 * ks, DESC_HI, kETK + 64 * i + 2 * ks, DESC_HI, ID_SM, 1u);
+              }
+            }
+            mma_commit(bar_w);
           }
-          mma_commit(bar_w);
+          __syncwarp();
         }
-        first_tile = false;
+        acc_g = 1u;
       }
     }
-    __syncwarp();
   } else {
     // =====================================================================================
     // epilogue warps
     // =====================================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int q = warp & 3, h = warp >> 2;
     const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;   // this thread's two points (tile rows)
     const int cq = 2 * (lane & 3);                      // column offset inside an 8-column block
