@@ -271,7 +271,7 @@ __device__ __forceinline__ bool elect_one() {
 //   bar_w         commit       issuer -> epilogue : every MMA that reads the operand sets has completed
 // Accumulator regions ping-pong (R0/R1) so that the MMAs of step s+1 run while step s is still
 // being read; a step's K-step-j MMAs are issued as soon as chunk j has been written.
-template <int D, int ORDER>
+template <int D, int ORDER, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   constexpr int ND = (ORDER >= 1) ? D : 0;
   constexpr int LAP = (ORDER == 2) ? 1 : 0;
@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_chunk + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_h = a.n_h, act = a.act;
+  const int n_h = a.n_h;
+  constexpr int act = ACT;
   const bool do_bwd = a.want_grad != 0;
   const uint32_t sbase = smem_u32(sm);
   const uint32_t sT1 = sbase + SM::off_T1, sT2 = sbase + SM::off_T2, sWT = sbase + SM::off_W;
@@ -675,6 +676,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       // ================= reverse sweep =================
       for (int l = n_h - 1; l >= 0; --l) {
         const bool top = (l == n_h - 1);
+        // stash of this layer (activation values, pre-activation jets) and of the layer below (whose
+        // activations are this layer's wgrad operand): chunk 0 now, chunk j+1 while chunk j computes
+        float4 cur[NV], prv[NV];
+        {
+          cur[0] = __ldcg(stash_at(l, 0, 0)); cur[1] = __ldcg(stash_at(l, 0, 1));
+          if (l >= 1) {
+#pragma unroll
+            for (int v = 2; v < NV; ++v) cur[v] = __ldcg(stash_at(l, 0, v));
+            prv[0] = __ldcg(stash_at(l - 1, 0, 0)); prv[1] = __ldcg(stash_at(l - 1, 0, 1));
+            if (l >= 2) {
+#pragma unroll
+              for (int v = 2; v < NV; ++v) prv[v] = __ldcg(stash_at(l - 1, 0, v));
+            }
+          }
+        }
         if (!top) {
           mbar_wait(bar_d, ph_d);   // Ab_l is complete
           ph_d ^= 1;
@@ -683,6 +699,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;
+          float4 ncur[NV], nprv[NV];
+          if (j < 3) {
+            ncur[0] = __ldcg(stash_at(l, j + 1, 0)); ncur[1] = __ldcg(stash_at(l, j + 1, 1));
+            if (l >= 1) {
+#pragma unroll
+              for (int v = 2; v < NV; ++v) ncur[v] = __ldcg(stash_at(l, j + 1, v));
+              nprv[0] = __ldcg(stash_at(l - 1, j + 1, 0)); nprv[1] = __ldcg(stash_at(l - 1, j + 1, 1));
+              if (l >= 2) {
+#pragma unroll
+                for (int v = 2; v < NV; ++v) nprv[v] = __ldcg(stash_at(l - 1, j + 1, v));
+              }
+            }
+          }
           float ab[C][4];
           if (top) {
             const float w0v = sWL[u0], w1v = sWL[u0 + 1];
@@ -696,15 +725,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(reg, c) + ((32 * q) << 16) + 16 * j + 8 * h, ab[c]);
             tmem_ld_wait();
           }
-          // stash of this layer: activation values and pre-activation jets
-          const float4 q0 = __ldcg(stash_at(l, j, 0)), q1 = __ldcg(stash_at(l, j, 1));
-          const float sv0[4] = {q0.x, q0.y, q0.z, q0.w}, sv1[4] = {q1.x, q1.y, q1.z, q1.w};
+          const float sv0[4] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w}, sv1[4] = {cur[1].x, cur[1].y, cur[1].z, cur[1].w};
           float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
           if (l >= 1) {
 #pragma unroll
             for (int c = 1; c < C; ++c) {
-              const float4 t = __ldcg(stash_at(l, j, 1 + c));
-              zj[c][0] = t.x; zj[c][1] = t.y; zj[c][2] = t.z; zj[c][3] = t.w;
+              zj[c][0] = cur[1 + c].x; zj[c][1] = cur[1 + c].y; zj[c][2] = cur[1 + c].z; zj[c][3] = cur[1 + c].w;
             }
           } else {
 #pragma unroll
@@ -757,14 +783,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           store_chunk(sT2, j, zb);
           if (l >= 1) {
             // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
-            const float4 p0 = __ldcg(stash_at(l - 1, j, 0)), p1 = __ldcg(stash_at(l - 1, j, 1));
-            const float pv0[4] = {p0.x, p0.y, p0.z, p0.w}, pv1[4] = {p1.x, p1.y, p1.z, p1.w};
+            const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
             float zp[C][4];
             if (l - 1 >= 1) {
 #pragma unroll
               for (int c = 1; c < C; ++c) {
-                const float4 t = __ldcg(stash_at(l - 1, j, 1 + c));
-                zp[c][0] = t.x; zp[c][1] = t.y; zp[c][2] = t.z; zp[c][3] = t.w;
+                zp[c][0] = prv[1 + c].x; zp[c][1] = prv[1 + c].y; zp[c][2] = prv[1 + c].z; zp[c][3] = prv[1 + c].w;
               }
             } else {
 #pragma unroll
@@ -792,6 +816,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             store_chunk(sT1, j, ap);
           }
           chunk_done(j);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { cur[v] = ncur[v]; prv[v] = nprv[v]; }
         }
         if (!top) reg ^= 1;
         w_pending = true;   // the issuer commits bar_w after this step's wgrad / first-layer MMAs
@@ -950,38 +976,43 @@ struct TcPlan {
 
 static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
 
-template <int D, int ORDER>
+template <int D, int ORDER, int ACT>
 static cudaError_t launch_one(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
   constexpr int C = 1 + (ORDER >= 1 ? D : 0) + (ORDER == 2);
   if constexpr (C > MAXC) {
     return cudaErrorInvalidValue;
   } else {
     const int smem = SmemMap<D, C>::total;
-    cudaError_t err = cudaFuncSetAttribute(tc_kernel<D, ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t err = cudaFuncSetAttribute(tc_kernel<D, ORDER, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
-    tc_kernel<D, ORDER><<<p.grid, NTHREADS, smem, st>>>(a);
+    tc_kernel<D, ORDER, ACT><<<p.grid, NTHREADS, smem, st>>>(a);
     return cudaGetLastError();
   }
 }
 
-static cudaError_t launch_tc(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
+template <int ACT>
+static cudaError_t launch_act(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
   switch (p.D * 3 + p.order) {
-    case 3: return launch_one<1, 0>(p, a, st);
-    case 4: return launch_one<1, 1>(p, a, st);
-    case 5: return launch_one<1, 2>(p, a, st);
-    case 6: return launch_one<2, 0>(p, a, st);
-    case 7: return launch_one<2, 1>(p, a, st);
-    case 8: return launch_one<2, 2>(p, a, st);
-    case 9: return launch_one<3, 0>(p, a, st);
-    case 10: return launch_one<3, 1>(p, a, st);
-    case 11: return launch_one<3, 2>(p, a, st);
-    case 12: return launch_one<4, 0>(p, a, st);
-    case 13: return launch_one<4, 1>(p, a, st);
-    case 14: return launch_one<4, 2>(p, a, st);
-    case 15: return launch_one<5, 0>(p, a, st);
-    case 16: return launch_one<5, 1>(p, a, st);
+    case 3: return launch_one<1, 0, ACT>(p, a, st);
+    case 4: return launch_one<1, 1, ACT>(p, a, st);
+    case 5: return launch_one<1, 2, ACT>(p, a, st);
+    case 6: return launch_one<2, 0, ACT>(p, a, st);
+    case 7: return launch_one<2, 1, ACT>(p, a, st);
+    case 8: return launch_one<2, 2, ACT>(p, a, st);
+    case 9: return launch_one<3, 0, ACT>(p, a, st);
+    case 10: return launch_one<3, 1, ACT>(p, a, st);
+    case 11: return launch_one<3, 2, ACT>(p, a, st);
+    case 12: return launch_one<4, 0, ACT>(p, a, st);
+    case 13: return launch_one<4, 1, ACT>(p, a, st);
+    case 14: return launch_one<4, 2, ACT>(p, a, st);
+    case 15: return launch_one<5, 0, ACT>(p, a, st);
+    case 16: return launch_one<5, 1, ACT>(p, a, st);
     default: return cudaErrorInvalidValue;
   }
+}
+
+static cudaError_t launch_tc(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
+  return a.act == PDE_ACT_TANH ? launch_act<1>(p, a, st) : launch_act<0>(p, a, st);
 }
 
 static int path_override() {
