@@ -70,15 +70,13 @@ __device__ __forceinline__ void act_from_stash(int act, float v0, float v1, floa
     s0 = v0; s1 = v1; s2 = -2.f * v0 * v1; s3 = -2.f * v1 * (1.f - 3.f * v0 * v0);
   }
 }
-// sin and cos to ~1 ulp for |z| < 2^15 (three-term Cody-Waite reduction by pi/2, minimax
-// polynomials on [-pi/4, pi/4]); larger arguments take the library path
+// sin and cos to ~1 ulp for |z| <= 2^15: magic-number rounding of z * 2/pi, three-term Cody-Waite
+// reduction by pi/2, minimax polynomials on [-pi/4, pi/4], quadrant fix-up on the sign bits.
+// (Callers route larger arguments to the library sincosf.)
 __device__ __forceinline__ void sincos_cw(float z, float& s, float& c) {
-  if (fabsf(z) > 32768.f) {
-    sincosf(z, &s, &c);
-    return;
-  }
-  const float kf = rintf(z * 0.636619772f);
-  const int k = __float2int_rn(kf);
+  const float t = fmaf(z, 0.636619772f, 12582912.f);   // 1.5 * 2^23: the low mantissa bits hold round(z * 2/pi)
+  const uint32_t k = __float_as_uint(t);
+  const float kf = t - 12582912.f;
   float r = fmaf(kf, -1.57079601e+00f, z);
   r = fmaf(kf, -3.13916473e-07f, r);
   r = fmaf(kf, -5.39030253e-15f, r);
@@ -90,13 +88,16 @@ __device__ __forceinline__ void sincos_cw(float z, float& s, float& c) {
   cp = fmaf(cp, r2, 4.16666457e-2f);
   cp = fmaf(cp, r2, -0.5f);
   cp = fmaf(cp, r2, 1.0f);
-  const float a = (k & 1) ? cp : sp, b = (k & 1) ? sp : cp;
-  s = (k & 2) ? -a : a;
-  c = ((k + 1) & 2) ? -b : b;
+  const bool odd = (k & 1u) != 0;
+  const float a = odd ? cp : sp, b = odd ? sp : cp;
+  s = __uint_as_float(__float_as_uint(a) ^ ((k & 2u) << 30));
+  c = __uint_as_float(__float_as_uint(b) ^ (((k + 1u) & 2u) << 30));
 }
-__device__ __forceinline__ void act_eval(int act, float z, float& v0, float& v1) {
+// `big`: warp-uniform flag "some |z| of this chunk is outside the fast range"
+__device__ __forceinline__ void act_eval(int act, float z, bool big, float& v0, float& v1) {
   if (act == 0) {
-    sincos_cw(z, v0, v1);
+    if (big) sincosf(z, &v0, &v1);
+    else sincos_cw(z, v0, v1);
   } else {
     v0 = tanhf(z); v1 = 1.f - v0 * v0;
   }
@@ -575,10 +576,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           ph_d ^= 1;
           tc_fence_after();
         }
+        float z[C][4];   // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]; chunk j+1 is fetched while chunk j is processed
+        const uint32_t zsrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
+        if (l >= 1) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), z[c]);
+        }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;   // this thread's columns u0, u0+1
-          float z[C][4];                        // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]
           if (l == 0) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -592,16 +598,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               if constexpr (LAP) z[1 + ND][e] = 0.f;
             }
           } else {
-#pragma unroll
-            for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(reg, c) + ((32 * q) << 16) + 16 * j + 8 * h, z[c]);
             tmem_ld_wait();
             const float b0v = sB[l * 64 + u0], b1v = sB[l * 64 + u0 + 1];
             z[0][0] += b0v; z[0][1] += b1v; z[0][2] += b0v; z[0][3] += b1v;
           }
           float av[C][4], sv0[4], sv1[4];
+          const bool big = (act == 0) && __any_sync(0xffffffffu, fmaxf(fmaxf(fabsf(z[0][0]), fabsf(z[0][1])), fmaxf(fabsf(z[0][2]), fabsf(z[0][3]))) > 32768.f);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            act_eval(act, z[0][e], sv0[e], sv1[e]);
+            act_eval(act, z[0][e], big, sv0[e], sv1[e]);
             float s0, s1, s2, s3;
             act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
             av[0][e] = s0;
@@ -620,6 +625,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
               for (int c = 1; c < C; ++c) __stcg(stash_at(l, j, 1 + c), make_float4(z[c][0], z[c][1], z[c][2], z[c][3]));
             }
+          }
+          if (l >= 1 && j < 3) {
+            // z has been consumed: fetch the accumulators of the next chunk now
+#pragma unroll
+            for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), z[c]);
           }
           if (!last) {
             store_chunk(sT1, j, av);
@@ -676,43 +686,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       // ================= reverse sweep =================
       for (int l = n_h - 1; l >= 0; --l) {
         const bool top = (l == n_h - 1);
-        // stash of this layer (activation values, pre-activation jets) and of the layer below (whose
-        // activations are this layer's wgrad operand): chunk 0 now, chunk j+1 while chunk j computes
+        // Stash of this layer (activation values, pre-activation jets) and of the layer below (whose
+        // activations are this layer's wgrad operand).  Software pipeline: the registers of chunk j+1
+        // are fetched as soon as chunk j has consumed them (no rotation copies).
         float4 cur[NV], prv[NV];
-        {
-          cur[0] = __ldcg(stash_at(l, 0, 0)); cur[1] = __ldcg(stash_at(l, 0, 1));
+        auto load_cur = [&](int j) {
+          cur[0] = __ldcg(stash_at(l, j, 0)); cur[1] = __ldcg(stash_at(l, j, 1));
           if (l >= 1) {
 #pragma unroll
-            for (int v = 2; v < NV; ++v) cur[v] = __ldcg(stash_at(l, 0, v));
-            prv[0] = __ldcg(stash_at(l - 1, 0, 0)); prv[1] = __ldcg(stash_at(l - 1, 0, 1));
+            for (int v = 2; v < NV; ++v) cur[v] = __ldcg(stash_at(l, j, v));
+          }
+        };
+        auto load_prv = [&](int j) {
+          if (l >= 1) {
+            prv[0] = __ldcg(stash_at(l - 1, j, 0)); prv[1] = __ldcg(stash_at(l - 1, j, 1));
             if (l >= 2) {
 #pragma unroll
-              for (int v = 2; v < NV; ++v) prv[v] = __ldcg(stash_at(l - 1, 0, v));
+              for (int v = 2; v < NV; ++v) prv[v] = __ldcg(stash_at(l - 1, j, v));
             }
           }
-        }
+        };
+        load_cur(0);
+        load_prv(0);
         if (!top) {
           mbar_wait(bar_d, ph_d);   // Ab_l is complete
           ph_d ^= 1;
           tc_fence_after();
         }
+        float ab[C][4];
+        const uint32_t absrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
+        if (!top) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), ab[c]);
+        }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;
-          float4 ncur[NV], nprv[NV];
-          if (j < 3) {
-            ncur[0] = __ldcg(stash_at(l, j + 1, 0)); ncur[1] = __ldcg(stash_at(l, j + 1, 1));
-            if (l >= 1) {
-#pragma unroll
-              for (int v = 2; v < NV; ++v) ncur[v] = __ldcg(stash_at(l, j + 1, v));
-              nprv[0] = __ldcg(stash_at(l - 1, j + 1, 0)); nprv[1] = __ldcg(stash_at(l - 1, j + 1, 1));
-              if (l >= 2) {
-#pragma unroll
-                for (int v = 2; v < NV; ++v) nprv[v] = __ldcg(stash_at(l - 1, j + 1, v));
-              }
-            }
-          }
-          float ab[C][4];
           if (top) {
             const float w0v = sWL[u0], w1v = sWL[u0 + 1];
 #pragma unroll
@@ -721,58 +730,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               ab[c][0] = w0v * n0; ab[c][1] = w1v * n0; ab[c][2] = w0v * n1; ab[c][3] = w1v * n1;
             }
           } else {
-#pragma unroll
-            for (int c = 0; c < C; ++c) tmem_ld_16x256b(d_addr(reg, c) + ((32 * q) << 16) + 16 * j + 8 * h, ab[c]);
             tmem_ld_wait();
           }
-          const float sv0[4] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w}, sv1[4] = {cur[1].x, cur[1].y, cur[1].z, cur[1].w};
-          float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
-          if (l >= 1) {
+          float zb[C][4];
+          {
+            const float sv0[4] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w}, sv1[4] = {cur[1].x, cur[1].y, cur[1].z, cur[1].w};
+            float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
+            if (l >= 1) {
 #pragma unroll
-            for (int c = 1; c < C; ++c) {
-              zj[c][0] = cur[1 + c].x; zj[c][1] = cur[1 + c].y; zj[c][2] = cur[1 + c].z; zj[c][3] = cur[1 + c].w;
+              for (int c = 1; c < C; ++c) {
+                zj[c][0] = cur[1 + c].x; zj[c][1] = cur[1 + c].y; zj[c][2] = cur[1 + c].z; zj[c][3] = cur[1 + c].w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int u = u0 + (e & 1);
+#pragma unroll
+                for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[i * 64 + u];
+                if constexpr (LAP) zj[1 + ND][e] = 0.f;
+              }
             }
-          } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int u = u0 + (e & 1);
+              float s0, s1, s2, s3;
+              act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
+              float t0 = s1 * ab[0][e];
+              float abL = 0.f;
+              if constexpr (LAP) abL = ab[1 + ND][e];
+              float S = 0.f;
 #pragma unroll
-              for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[i * 64 + u];
-              if constexpr (LAP) zj[1 + ND][e] = 0.f;
+              for (int i = 0; i < ND; ++i) {
+                const float zi = zj[1 + i][e];
+                t0 = fmaf(s2 * zi, ab[1 + i][e], t0);
+                S = fmaf(zi, zi, S);
+                float ti = s1 * ab[1 + i][e];
+                if constexpr (LAP) ti = fmaf(2.f * s2 * zi, abL, ti);
+                zb[1 + i][e] = ti;
+              }
+              if constexpr (LAP) {
+                t0 = fmaf(fmaf(s2, zj[1 + ND][e], s3 * S), abL, t0);
+                zb[1 + ND][e] = s1 * abL;
+              }
+              zb[0][e] = t0;
+              if (top) {
+                // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
+                const int r = (e < 2) ? r0 : r1;
+                float g = sNb[r * C] * s0;
+#pragma unroll
+                for (int i = 0; i < ND; ++i) g = fmaf(sNb[r * C + 1 + i], s1 * zj[1 + i][e], g);
+                if constexpr (LAP) g = fmaf(sNb[r * C + 1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
+                gwl[j][e & 1] += g;
+              }
             }
           }
-          float zb[C][4];
+          if (j < 3) {
+            // ab and cur have been consumed: fetch chunk j+1
+            if (!top) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float s0, s1, s2, s3;
-            act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
-            float t0 = s1 * ab[0][e];
-            float abL = 0.f;
-            if constexpr (LAP) abL = ab[1 + ND][e];
-            float S = 0.f;
-#pragma unroll
-            for (int i = 0; i < ND; ++i) {
-              const float zi = zj[1 + i][e];
-              t0 = fmaf(s2 * zi, ab[1 + i][e], t0);
-              S = fmaf(zi, zi, S);
-              float ti = s1 * ab[1 + i][e];
-              if constexpr (LAP) ti = fmaf(2.f * s2 * zi, abL, ti);
-              zb[1 + i][e] = ti;
+              for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), ab[c]);
             }
-            if constexpr (LAP) {
-              t0 = fmaf(fmaf(s2, zj[1 + ND][e], s3 * S), abL, t0);
-              zb[1 + ND][e] = s1 * abL;
-            }
-            zb[0][e] = t0;
-            if (top) {
-              // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
-              const int r = (e < 2) ? r0 : r1;
-              float g = sNb[r * C] * s0;
-#pragma unroll
-              for (int i = 0; i < ND; ++i) g = fmaf(sNb[r * C + 1 + i], s1 * zj[1 + i][e], g);
-              if constexpr (LAP) g = fmaf(sNb[r * C + 1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
-              gwl[j][e & 1] += g;
-            }
+            load_cur(j + 1);
           }
           if (j == 0 && w_pending) {
             // the previous layer's wgrad still reads both operand sets: wait for it before the first store
@@ -783,41 +800,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           store_chunk(sT2, j, zb);
           if (l >= 1) {
             // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
-            const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
-            float zp[C][4];
-            if (l - 1 >= 1) {
+            float ap[C][4];
+            {
+              const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
+              float zp[C][4];
+              if (l - 1 >= 1) {
 #pragma unroll
-              for (int c = 1; c < C; ++c) {
-                zp[c][0] = prv[1 + c].x; zp[c][1] = prv[1 + c].y; zp[c][2] = prv[1 + c].z; zp[c][3] = prv[1 + c].w;
+                for (int c = 1; c < C; ++c) {
+                  zp[c][0] = prv[1 + c].x; zp[c][1] = prv[1 + c].y; zp[c][2] = prv[1 + c].z; zp[c][3] = prv[1 + c].w;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int u = u0 + (e & 1);
+#pragma unroll
+                  for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
+                  if constexpr (LAP) zp[1 + ND][e] = 0.f;
+                }
               }
-            } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int u = u0 + (e & 1);
+                float s0, s1, s2, s3;
+                act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
+                ap[0][e] = s0;
+                float S = 0.f;
 #pragma unroll
-                for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
-                if constexpr (LAP) zp[1 + ND][e] = 0.f;
+                for (int i = 0; i < ND; ++i) {
+                  ap[1 + i][e] = s1 * zp[1 + i][e];
+                  S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
+                }
+                if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
               }
             }
-            float ap[C][4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float s0, s1, s2, s3;
-              act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
-              ap[0][e] = s0;
-              float S = 0.f;
-#pragma unroll
-              for (int i = 0; i < ND; ++i) {
-                ap[1 + i][e] = s1 * zp[1 + i][e];
-                S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
-              }
-              if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
-            }
+            if (j < 3) load_prv(j + 1);
             store_chunk(sT1, j, ap);
           }
           chunk_done(j);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { cur[v] = ncur[v]; prv[v] = nprv[v]; }
         }
         if (!top) reg ^= 1;
         w_pending = true;   // the issuer commits bar_w after this step's wgrad / first-layer MMAs
