@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 #include "pde_launch.h"
 #include "pde_tc.h"
@@ -569,23 +570,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         for (int c = 0; c < C; ++c) outacc[r][c] = 0.f;
 
       // ================= forward =================
-      for (int l = 0; l < n_h; ++l) {
-        const bool last = (l == n_h - 1);
-        if (l >= 1) {
+      auto fwd_layer = [&](auto l0_tag, auto last_tag, const int l) {
+        constexpr bool L0 = decltype(l0_tag)::value, LAST = decltype(last_tag)::value;
+        if constexpr (!L0) {
           mbar_wait(bar_d, ph_d);
           ph_d ^= 1;
           tc_fence_after();
         }
         float z[C][4];   // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]; chunk j+1 is fetched while chunk j is processed
         const uint32_t zsrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
-        if (l >= 1) {
+        if constexpr (!L0) {
 #pragma unroll
           for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), z[c]);
         }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;   // this thread's columns u0, u0+1
-          if (l == 0) {
+          if constexpr (L0) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int row = (e < 2) ? r0 : r1, u = u0 + (e & 1);
@@ -621,17 +622,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           if (do_bwd) {
             __stcg(stash_at(l, j, 0), make_float4(sv0[0], sv0[1], sv0[2], sv0[3]));
             __stcg(stash_at(l, j, 1), make_float4(sv1[0], sv1[1], sv1[2], sv1[3]));
-            if (l >= 1) {
+            if constexpr (!L0) {
 #pragma unroll
               for (int c = 1; c < C; ++c) __stcg(stash_at(l, j, 1 + c), make_float4(z[c][0], z[c][1], z[c][2], z[c][3]));
             }
           }
-          if (l >= 1 && j < 3) {
+          if (!L0 && j < 3) {
             // z has been consumed: fetch the accumulators of the next chunk now
 #pragma unroll
             for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), z[c]);
           }
-          if (!last) {
+          if constexpr (!LAST) {
             store_chunk(sT1, j, av);
             chunk_done(j);
           } else {
@@ -643,8 +644,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
           }
         }
-        if (l >= 1) reg ^= 1;
-      }
+        if constexpr (!L0) reg ^= 1;
+      };
+      fwd_layer(std::true_type{}, std::false_type{}, 0);
+      for (int l = 1; l < n_h - 1; ++l) fwd_layer(std::false_type{}, std::false_type{}, l);
+      fwd_layer(std::false_type{}, std::true_type{}, n_h - 1);
 
       // ================= output layer + envelope + residual program =================
 #pragma unroll
@@ -684,23 +688,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       if (!do_bwd) continue;
 
       // ================= reverse sweep =================
-      for (int l = n_h - 1; l >= 0; --l) {
-        const bool top = (l == n_h - 1);
+      auto bwd_layer = [&](auto top_tag, auto lk_tag, const int l) {
+        constexpr bool TOP = decltype(top_tag)::value;
+        constexpr int LK = decltype(lk_tag)::value;   // 0: first layer, 1: l == 1, 2: l >= 2
         // Stash of this layer (activation values, pre-activation jets) and of the layer below (whose
         // activations are this layer's wgrad operand).  Software pipeline: the registers of chunk j+1
         // are fetched as soon as chunk j has consumed them (no rotation copies).
         float4 cur[NV], prv[NV];
         auto load_cur = [&](int j) {
           cur[0] = __ldcg(stash_at(l, j, 0)); cur[1] = __ldcg(stash_at(l, j, 1));
-          if (l >= 1) {
+          if constexpr (LK >= 1) {
 #pragma unroll
             for (int v = 2; v < NV; ++v) cur[v] = __ldcg(stash_at(l, j, v));
           }
         };
         auto load_prv = [&](int j) {
-          if (l >= 1) {
+          if constexpr (LK >= 1) {
             prv[0] = __ldcg(stash_at(l - 1, j, 0)); prv[1] = __ldcg(stash_at(l - 1, j, 1));
-            if (l >= 2) {
+            if constexpr (LK >= 2) {
 #pragma unroll
               for (int v = 2; v < NV; ++v) prv[v] = __ldcg(stash_at(l - 1, j, v));
             }
@@ -708,21 +713,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         };
         load_cur(0);
         load_prv(0);
-        if (!top) {
+        if constexpr (!TOP) {
           mbar_wait(bar_d, ph_d);   // Ab_l is complete
           ph_d ^= 1;
           tc_fence_after();
         }
         float ab[C][4];
         const uint32_t absrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
-        if (!top) {
+        if constexpr (!TOP) {
 #pragma unroll
           for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), ab[c]);
         }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;
-          if (top) {
+          if constexpr (TOP) {
             const float w0v = sWL[u0], w1v = sWL[u0 + 1];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -736,7 +741,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           {
             const float sv0[4] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w}, sv1[4] = {cur[1].x, cur[1].y, cur[1].z, cur[1].w};
             float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
-            if (l >= 1) {
+            if constexpr (LK >= 1) {
 #pragma unroll
               for (int c = 1; c < C; ++c) {
                 zj[c][0] = cur[1 + c].x; zj[c][1] = cur[1 + c].y; zj[c][2] = cur[1 + c].z; zj[c][3] = cur[1 + c].w;
@@ -772,7 +777,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
                 zb[1 + ND][e] = s1 * abL;
               }
               zb[0][e] = t0;
-              if (top) {
+              if constexpr (TOP) {
                 // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
                 const int r = (e < 2) ? r0 : r1;
                 float g = sNb[r * C] * s0;
@@ -785,7 +790,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
           if (j < 3) {
             // ab and cur have been consumed: fetch chunk j+1
-            if (!top) {
+            if constexpr (!TOP) {
 #pragma unroll
               for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), ab[c]);
             }
@@ -798,13 +803,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             w_pending = false;
           }
           store_chunk(sT2, j, zb);
-          if (l >= 1) {
+          if constexpr (LK >= 1) {
             // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
             float ap[C][4];
             {
               const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
               float zp[C][4];
-              if (l - 1 >= 1) {
+              if constexpr (LK >= 2) {
 #pragma unroll
                 for (int c = 1; c < C; ++c) {
                   zp[c][0] = prv[1 + c].x; zp[c][1] = prv[1 + c].y; zp[c][2] = prv[1 + c].z; zp[c][3] = prv[1 + c].w;
@@ -837,9 +842,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
           chunk_done(j);
         }
-        if (!top) reg ^= 1;
+        if constexpr (!TOP) reg ^= 1;
         w_pending = true;   // the issuer commits bar_w after this step's wgrad / first-layer MMAs
-      }
+      };
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+      using I2 = std::integral_constant<int, 2>;
+      if (n_h - 1 >= 2) bwd_layer(std::true_type{}, I2{}, n_h - 1);
+      else bwd_layer(std::true_type{}, I1{}, n_h - 1);
+      for (int l = n_h - 2; l >= 2; --l) bwd_layer(std::false_type{}, I2{}, l);
+      if (n_h - 2 >= 1) bwd_layer(std::false_type{}, I1{}, 1);
+      bwd_layer(std::false_type{}, I0{}, 0);
     }
 
     // ================= per-CTA results =================
