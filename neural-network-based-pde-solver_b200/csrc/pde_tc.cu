@@ -230,6 +230,8 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
   asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
+// fire-and-forget fp32 add (round to nearest) to global memory
+__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // UMMA descriptors as "constant high word + 14-bit start address (16-byte units) in the low word":
@@ -311,11 +313,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   for (int i = tid; i < 64 + 1; i += NTHREADS) sWL[i] = a.params[D * 64 + n_h * 64 + i];
   for (int i = tid; i < (1024 * (D > 0 ? D : 1)) / 4; i += NTHREADS) {
     const int n = i / 256, w = i % 256;  // tile n, 32-bit word w: row = w / 32
-    reinterpret_cast<uint32_t*>(sm + SM::off_E)[i] = ((w >> 5) == n) ? 0x3F803F80u : 0u;
+    reinterpret_cast<uint32_t*>(sm + SM::off_E)[i] = ((w >> 5) == n) ? ONE_X2 : 0u;
   }
   for (int i = tid; i < 512; i += NTHREADS) {
     const int t = i / 256, w = i % 256;
-    reinterpret_cast<uint32_t*>(sm + SM::off_XT)[i] = (t == 0 && (w >> 5) == D) ? 0x3F803F80u : 0u;
+    reinterpret_cast<uint32_t*>(sm + SM::off_XT)[i] = (t == 0 && (w >> 5) == D) ? ONE_X2 : 0u;
   }
   {
     // resident: every hidden layer's W; otherwise W_1 (later layers are streamed by the issuer)
@@ -366,7 +368,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       const uint32_t kXTK = (sXT >> 4) | DESC_K_LBO, kETK = (sET >> 4) | DESC_K_LBO;
       uint32_t ph_chunk = 0, ph_own = 0, ph_wt = 0;
       int reg = 0;   // region the next D-producing GEMM writes
-      uint32_t acc_g = 0;   // 0 until the gradient accumulators have been initialised by the first tile
       int cur_w = 1;   // layer whose W sits in the single buffer (non-resident W)
       // make W_l the resident tile pair: drain my MMAs (they may read the buffer), then one bulk copy
       auto need_w = [&](int l) {
@@ -440,7 +441,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           __syncwarp();
           ph_chunk ^= 1;
           reg ^= 1;
-          // wgrad: gW_l += sum_c Zb_{l,c}^T A_{l-1,c}   (K = 64 points);  bias: gb_l += Zb_{l,0}^T 1
+          // wgrad: gW_l(tile) = sum_c Zb_{l,c}^T A_{l-1,c}   (K = 64 points);  bias: gb_l(tile) = Zb_{l,0}^T 1.
+          // The accumulators start from zero every tile (the epilogue adds them to the running fp32
+          // sums, see flush_grads) and the small cross terms go first: the tensor core truncates
+          // when it accumulates, so the error of an update scales with the accumulator's magnitude.
           if (elect_one()) {
             const int sl = l - 1;
             const uint32_t d = tm + ((16 * (sl & 1)) << 16) + COL_G + 64 * (sl >> 1);
@@ -450,17 +454,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t zh = kT2M + (2 * c) * TD + 128 * ks, zl = zh + TD;
                 const uint32_t ah = kT1M + (2 * c) * TD + 128 * ks, al = ah + TD;
-                mma_k(d, zh, DESC_HI, ah, DESC_HI, ID_WG, (c == 0 && ks == 0) ? acc_g : 1u);
-                mma_k(d, zl, DESC_HI, ah, DESC_HI, ID_WG, 1u);
+                mma_k(d, zl, DESC_HI, ah, DESC_HI, ID_WG, (c == 0 && ks == 0) ? 0u : 1u);
                 mma_k(d, zh, DESC_HI, al, DESC_HI, ID_WG, 1u);
               }
             }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_k(d, kT2M + (2 * c) * TD + 128 * ks, DESC_HI, kT1M + (2 * c) * TD + 128 * ks, DESC_HI, ID_WG, 1u);
+            }
             const uint32_t db = tm + (16u << 16) + COL_SMALL + 8 * l;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              mma_k(db, kT2M + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? acc_g : 1u);
-              mma_k(db, kT2M + TD + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, 1u);
-            }
+            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M + TD + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, 1u);
             mma_commit(bar_w);
           }
           __syncwarp();
@@ -475,23 +483,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             const uint32_t d = tm + (16u << 16) + COL_SMALL;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? acc_g : 1u);
-              mma_k(d, kT2M + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
+              mma_k(d, kT2M + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
               mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 64 + 2 * ks, DESC_HI, ID_SM, 1u);
             }
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                mma_k(d, kT2M + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK + 64 * i + 2 * ks, DESC_HI, ID_SM, 1u);
+              for (int ks = 0; ks < 4; ++ks)
                 mma_k(d, kT2M + (2 * (1 + i) + 1) * TD + 128 * ks, DESC_HI, kETK + 64 * i + 2 * ks, DESC_HI, ID_SM, 1u);
-              }
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
+#pragma unroll
+            for (int i = 0; i < ND; ++i) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                mma_k(d, kT2M + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK + 64 * i + 2 * ks, DESC_HI, ID_SM, 1u);
             }
             mma_commit(bar_w);
           }
           __syncwarp();
         }
-        acc_g = 1u;
       }
     }
   } else {
@@ -518,6 +530,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) gwl[j][0] = gwl[j][1] = 0.f;
     float gbl = 0.f;   // output bias gradient partial (program threads)
+    float adj_scale = 0.f;   // power-of-two scale of the adjoints of this CTA (0 = not chosen yet)
 
     // write 4 values (2 rows x 2 adjacent units) of every channel of chunk j into an operand set
     auto store_chunk = [&](uint32_t set, int j, const float (&v)[C][4]) {
@@ -538,6 +551,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     };
     auto stash_at = [&](int l, int j, int v) { return stash + ((l * 4 + j) * NEPI * NV + v) * 32; };
 
+    // The tensor core truncates (rounds toward zero) when it adds into an accumulator, so sums that
+    // run over many tiles are kept in fp32 with round-to-nearest here: each tile's weight / bias
+    // gradient accumulators start from zero and are added to this CTA's partial vector.  Every
+    // element of `part` is owned by one thread, so the fire-and-forget adds are applied in tile order
+    // (deterministic).  Precondition: bar_w of the tile's last step has been waited for.
+    float accW[3][4][4];   // running sums of gW_l: [layer slot][8-column block][fragment]
+    float accB[3][2];      // gb_l (lanes with lane % 4 == 0 of the h == 0 warps)
+    float acc0[4];         // [gW0 | gb0] fragment (h == 0 warps)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) accW[i][b][e] = 0.f;
+      accB[i][0] = accB[i][1] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc0[e] = 0.f;
+    auto flush_grads = [&]() {
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) {
+        if (sl + 1 < n_h) {
+          const uint32_t d = taddr_of(tmem, 32 * q + 16 * (sl & 1), COL_G + 64 * (sl >> 1));
+          float v[4][4], w[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) tmem_ld_16x256b(d + 32 * h + 8 * b, v[b]);
+          tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL + 8 * (sl + 1)), w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) accW[sl][b][e] += v[b][e];
+          accB[sl][0] += w[0];
+          accB[sl][1] += w[2];
+        }
+      }
+      {
+        float w[4];
+        tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL), w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc0[e] += w[e];
+      }
+      tc_fence_before();
+    };
+
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const long long base = (long long)tile * TP;
       // every MMA of the previous tile has completed before X^T / the operand sets are rewritten
@@ -545,6 +604,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         mbar_wait(bar_w, ph_w);
         ph_w ^= 1;
         w_pending = false;
+        tc_fence_after();
+        flush_grads();
       }
       named_sync(1, NEPI * 32);   // everyone is done with sX / sNb / sRed of the previous tile
       for (int i = tid; i < TP * D; i += NEPI * 32) {
@@ -668,21 +729,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         }
       }
       named_sync(1, NEPI * 32);
+      float nj[C];
       if (tid < TP) {
         const long long gp = base + tid;
-        float nj[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) nj[c] = sRed[tid * C + c] + sRed[(64 + tid) * C + c];
         nj[0] += sWL[64];
         if (gp < a.n) {
           program_point_lap<D, ORDER>(a, sX + tid * D, gp, nj, qs, gE);
-          gbl += nj[0];
         } else {
 #pragma unroll
           for (int c = 0; c < C; ++c) nj[c] = 0.f;
         }
+      }
+      if (!do_bwd) continue;
+      if (adj_scale == 0.f) {
+        // Power-of-two scale of this CTA's adjoints, from its first tile: the largest network-jet
+        // cotangent becomes 2..4, which keeps the 16-bit operand splits of the reverse sweep well
+        // inside their range whatever the size of the residual; undone when the gradients are written.
+        named_sync(1, NEPI * 32);   // sRed has been read
+        float mx = 0.f;
+        if (tid < TP) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) sNb[tid * C + c] = nj[c];
+          for (int c = 0; c < C; ++c) mx = fmaxf(mx, fabsf(nj[c]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) sRed[warp] = mx;
+        named_sync(1, NEPI * 32);
+        mx = fmaxf(sRed[0], sRed[1]);
+        int ex = 0;
+        if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &ex);
+        ex = max(-100, min(100, ex));
+        adj_scale = (mx > 0.f && mx < 3.0e38f) ? ldexpf(1.f, 2 - ex) : 1.f;
+      }
+      if (tid < TP) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          nj[c] *= adj_scale;
+          sNb[tid * C + c] = nj[c];
+        }
+        gbl += nj[0];
       }
       named_sync(1, NEPI * 32);
       if (!do_bwd) continue;
@@ -859,43 +946,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     if (w_pending) {
       mbar_wait(bar_w, ph_w);
       ph_w ^= 1;
+      tc_fence_after();
+      flush_grads();
     }
-    tc_fence_after();
     if (do_bwd) {
+      const float inv = (adj_scale != 0.f) ? 1.f / adj_scale : 1.f;   // exact: a power of two
       // hidden GEMM layers: gW_l at slot l-1, rows o = 16 q + lane/4 (+8), columns i
-      for (int l = 1; l < n_h; ++l) {
-        const int sl = l - 1;
-        float* gW = part + a.off_gW + (long long)sl * ((long long)HP * HP + HP);
-        const uint32_t d = taddr_of(tmem, 32 * q + 16 * (sl & 1), COL_G + 64 * (sl >> 1));
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          float v[4];
-          tmem_ld_16x256b(d + 32 * h + 8 * b, v);
-          tmem_ld_wait();
-          const int i0 = 32 * h + 8 * b + cq;
-          *reinterpret_cast<float2*>(gW + r0 * HP + i0) = make_float2(v[0], v[1]);
-          *reinterpret_cast<float2*>(gW + r1 * HP + i0) = make_float2(v[2], v[3]);
-        }
-        if (h == 0) {
-          float v[4];
-          tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL + 8 * l), v);
-          tmem_ld_wait();
-          if ((lane & 3) == 0) {
-            gW[HP * HP + r0] = v[0];
-            gW[HP * HP + r1] = v[2];
+      for (int sl = 0; sl < 3; ++sl) {
+        if (sl + 1 < n_h) {
+          float* gW = part + a.off_gW + (long long)sl * ((long long)HP * HP + HP);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int i0 = 32 * h + 8 * b + cq;
+            *reinterpret_cast<float2*>(gW + r0 * HP + i0) = make_float2(accW[sl][b][0] * inv, accW[sl][b][1] * inv);
+            *reinterpret_cast<float2*>(gW + r1 * HP + i0) = make_float2(accW[sl][b][2] * inv, accW[sl][b][3] * inv);
+          }
+          if (h == 0 && (lane & 3) == 0) {
+            gW[HP * HP + r0] = accB[sl][0] * inv;
+            gW[HP * HP + r1] = accB[sl][1] * inv;
           }
         }
       }
       if (h == 0) {
-        float v[4];
-        tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL), v);
-        tmem_ld_wait();
         // columns cq, cq+1 of [gW0 (D cols) | gb0]
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = cq + (e & 1), o = (e < 2) ? r0 : r1;
-          if (col < D) part[a.off_gW0 + o * D + col] = v[e];
-          else if (col == D) part[a.off_gb0 + o] = v[e];
+          if (col < D) part[a.off_gW0 + o * D + col] = acc0[e] * inv;
+          else if (col == D) part[a.off_gb0 + o] = acc0[e] * inv;
         }
       }
       // output layer: reduce the per-thread column partials over the 8 row groups of the warp ...
@@ -920,14 +999,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       }
       named_sync(1, NEPI * 32);
       // ... then over the four quarters in fixed order
-      if (tid < 64) part[a.off_gwL + tid] = (sRedW[tid] + sRedW[64 + tid]) + (sRedW[128 + tid] + sRedW[192 + tid]);
+      if (tid < 64) part[a.off_gwL + tid] = ((sRedW[tid] + sRedW[64 + tid]) + (sRedW[128 + tid] + sRedW[192 + tid])) * inv;
       named_sync(1, NEPI * 32);
       if (tid < 64) sRed[tid] = gbl;
       named_sync(1, NEPI * 32);
       if (tid == 0) {
         float v = 0.f;
         for (int i = 0; i < 64; ++i) v += sRed[i];
-        part[a.off_gbL] = v;
+        part[a.off_gbL] = v * inv;
       }
     }
     named_sync(1, NEPI * 32);

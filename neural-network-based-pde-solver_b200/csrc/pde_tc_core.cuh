@@ -97,9 +97,17 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, int ks) {
   return make_desc(tile_saddr + ks * 2048, 8192, 1024);
 }
 
-// instruction descriptor for kind::f16, bf16 x bf16 -> fp32
+// Operand number format of the split: fp16 (11 significand bits per part, the default) or bf16.
+// fp16 x 3 terms reproduces fp32 GEMMs to ~3e-7 but needs operands inside the fp16 range, which the
+// kernel arranges for the adjoints by a power-of-two scale; bf16 x 3 terms has fp32 range and ~3e-6.
+#ifndef PDE_TC_FP16
+#define PDE_TC_FP16 1
+#endif
+constexpr uint32_t ONE_X2 = PDE_TC_FP16 ? 0x3C003C00u : 0x3F803F80u;   // packed pair of 1.0
+
+// instruction descriptor for kind::f16, (fp16 | bf16) x same -> fp32
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+  return (1u << 4) | ((PDE_TC_FP16 ? 0u : 1u) << 7) | ((PDE_TC_FP16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
@@ -142,17 +150,36 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, float (&v)[8])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- bf16 hi/lo split of fp32 values:  x ~= hi + lo, each bf16 (round to nearest)
+// ---- hi/lo split of fp32 values:  x ~= hi + lo, each a 16-bit float (round to nearest)
 // packs (a -> low half, b -> high half)
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
   return d;
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+#if PDE_TC_FP16
+  hi = pack_f16x2(a, b);
+  float ha, hb;
+  asm("{\n\t"
+      ".reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "cvt.f32.f16 %0, l;\n\t"
+      "cvt.f32.f16 %1, h;\n\t"
+      "}"
+      : "=f"(ha), "=f"(hb)
+      : "r"(hi));
+  lo = pack_f16x2(a - ha, b - hb);
+#else
   hi = pack_bf16x2(a, b);
   float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
   lo = pack_bf16x2(a - ha, b - hb);
+#endif
 }
 
 }  // namespace tc

@@ -86,6 +86,27 @@ def case(d, w, depth, act, prog, env_kind, N, seed=0, path="tc"):
     return report(f"{path} d{d} w{w} depth{depth} {act} {prog} env={env_kind} N={N}", float(loss.item()), want, lin, gWs, gbs)
 
 
+def big_case(N=1 << 20, d=3, seed=3):
+    """tcgen05 fp32 vs the generic kernel in fp64 on the same large batch (accumulation accuracy)."""
+    rng = np.random.default_rng(seed)
+    net32, lin32, Ws, bs = make_net(d, 64, 5, "sin", rng)
+    net64, lin64, _, _ = make_net(d, 64, 5, "sin", np.random.default_rng(seed), dtype=torch.float64)
+    X = torch.rand(N, d, device="cuda", dtype=torch.float64) * 1.9 + 0.05
+    f = torch.randn(N, device="cuda", dtype=torch.float64)
+    X32 = X.float(); f32 = f.float()
+    X = X32.double(); f = f32.double()
+    espec = EnvelopeSpec(L.ENV_POLY, 0.0, 2.0)
+    os.environ["PDE_B200_PATH"] = "tc"
+    l32 = residual_means(net32, X32, ProgramSpec(L.PROG_PINN, -1.0), espec, f=f32)[0]
+    l32.backward()
+    os.environ["PDE_B200_PATH"] = "simt"
+    l64 = residual_means(net64, X, ProgramSpec(L.PROG_PINN, -1.0), espec, f=f)[0]
+    l64.backward()
+    torch.cuda.synchronize()
+    gWs = [l.weight.grad.cpu().numpy() for l in lin64]; gbs = [l.bias.grad.cpu().numpy() for l in lin64]
+    return report(f"tc fp32 vs generic fp64, d{d} N={N}", float(l32.item()), float(l64.item()), lin32, gWs, gbs)
+
+
 def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     ok = True
@@ -101,6 +122,7 @@ def main():
     ok &= case(2, 50, 5, "sin", "rayleigh", "poly", 1500)
     ok &= case(4, 33, 3, "tanh", "pinn", "none", 500)
     ok &= case(3, 64, 5, "sin", "pinn", "poly", 1000, path="simt")
+    ok &= big_case()
     print("ALL OK" if ok else "SOME BAD")
     return 0 if ok else 1
 

@@ -5,7 +5,17 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <cuda_fp16.h>
 #include "../neural-network-based-pde-solver_b200/csrc/pde_tc_core.cuh"
+#if PDE_TC_FP16
+typedef __half op_t;
+#define TO_OP(x) __float2half(x)
+#define FROM_OP(x) __half2float(x)
+#else
+typedef __nv_bfloat16 op_t;
+#define TO_OP(x) __float2bfloat16(x)
+#define FROM_OP(x) __bfloat162float(x)
+#endif
 
 using namespace pde::tc;
 
@@ -31,9 +41,9 @@ __global__ void __launch_bounds__(128, 1) probe(Args a) {
   // fill tiles: element (r, c) of the stored matrix
   for (int i = tid; i < 64 * 64; i += 128) {
     int r = i / 64, c = i % 64;
-    __nv_bfloat16 va = __float2bfloat16(a.A[i]), vb = __float2bfloat16(a.B[i]);
-    *reinterpret_cast<__nv_bfloat16*>(tA + tile_off(r, c >> 3) + (c & 7) * 2) = va;
-    *reinterpret_cast<__nv_bfloat16*>(tB + tile_off(r, c >> 3) + (c & 7) * 2) = vb;
+    op_t va = TO_OP(a.A[i]), vb = TO_OP(a.B[i]);
+    *reinterpret_cast<op_t*>(tA + tile_off(r, c >> 3) + (c & 7) * 2) = va;
+    *reinterpret_cast<op_t*>(tB + tile_off(r, c >> 3) + (c & 7) * 2) = vb;
   }
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -87,7 +97,7 @@ __global__ void __launch_bounds__(128, 1) probe(Args a) {
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
-static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+static float bf(float x) { return FROM_OP(TO_OP(x)); }
 
 int main() {
   std::vector<float> A(4096), B(4096);
