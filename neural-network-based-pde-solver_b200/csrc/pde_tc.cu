@@ -221,7 +221,8 @@ struct SmemMap {
   static constexpr int off_X = off_par + par_floats * 4;  // X tile [64][D]
   static constexpr int off_nb = off_X + 64 * D * 4;       // cotangents of the network jets [64][C]
   static constexpr int off_red = off_nb + 64 * C * 4;     // output-layer partial sums [2][64][C]
-  static constexpr int off_bar = off_red + 2 * 64 * C * 4;
+  static constexpr int red_floats = (2 * 64 * C > 256) ? 2 * 64 * C : 256;   // also [4][64] at the end
+  static constexpr int off_bar = off_red + red_floats * 4;
   static constexpr int total = off_bar + 128;
 };
 
@@ -1190,8 +1191,15 @@ static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl) {
 
 }  // namespace tc
 
+// The Rayleigh quotient's gradient is a difference of two nearly parallel vectors, which amplifies
+// the 1e-6 rounding of the split GEMMs towards the 1e-5 bar; it is served by the generic fp32 kernel
+// unless the tensor-core path is forced (PDE_B200_PATH=tc).
+static bool program_ok(const pde_program* prog) {
+  return prog && (prog->kind != PDE_PROG_RAYLEIGH || tc::path_override() == 1);
+}
+
 bool tc_supported(const pde_net* net, const pde_program* prog, long long n_points) {
-  if (!prog) return false;
+  if (!program_ok(prog)) return false;
   const int order = pde_program_order(prog->kind);
   tc::TcPlan p;
   return tc::make_plan(net, order, n_points, &p) == PDE_OK;
@@ -1212,6 +1220,7 @@ int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde
   if (!net || !prog) return PDE_ERR_INVALID;
   const int order = pde_program_order(prog->kind);
   if (order < 0) return PDE_ERR_INVALID;
+  if (!program_ok(prog)) return PDE_ERR_UNSUPPORTED;
   TcPlan p;
   int rc = make_plan(net, order, n_points, &p);
   if (rc) return rc;

@@ -195,6 +195,24 @@ def _all_reduce(t, group):
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
+def combine_forward(buf, nparam, n_tot, group, fused):
+    """Cross-rank step of a residual evaluation.  ``buf`` = [grad (nparam) | dE (1) | sums (K)] of this
+    rank, the gradient part already carrying 1/N_global.  One all-reduce (the whole buffer when the
+    reverse sweep was fused into the same launch, else the sums only) makes every rank hold the
+    single-big-batch values; returns the means.  (sums and gradient vectors are
+    reduced, never per-rank losses.)"""
+    if group is not None:
+        _all_reduce(buf if fused else buf[nparam + 1:], group)
+    return buf[nparam + 1:] / n_tot
+
+
+def combine_backward(buf, nparam, group):
+    """Cross-rank step of the seeded reverse sweep (functions of means): all-reduce [grad | dE]."""
+    if group is not None:
+        _all_reduce(buf[:nparam + 1], group)
+    return buf[:nparam], buf[nparam]
+
+
 # ---------------------------------------------------------------------------------------------
 # network jets
 # ---------------------------------------------------------------------------------------------
@@ -288,9 +306,7 @@ class _Residual(torch.autograd.Function):
                                                1.0 / n_tot, sptr, gptr, eptr, ws.data_ptr(), ws.numel(), _stream(dev)),
                     "pde_residual_loss_grad")
         _LAST_PATH = "tcgen05" if lib.pde_query_path(C.byref(cnet), C.byref(prog), n) == 1 else "simt_fma"
-        if group is not None:
-            _all_reduce(buf if fused else buf[nparam + 1:], group)
-        means = buf[nparam + 1:] / n_tot
+        means = combine_forward(buf, nparam, n_tot, group, fused)
         ctx.fused = fused
         ctx.has_energy = energy is not None
         if fused:
@@ -338,10 +354,9 @@ class _Residual(torch.autograd.Function):
                                                    buf.data_ptr() + (nparam + 1) * buf.element_size(), buf.data_ptr(),
                                                    buf.data_ptr() + nparam * buf.element_size(), ws.data_ptr(),
                                                    ws.numel(), _stream(dev)), "pde_residual_loss_grad")
-            if group is not None:
-                _all_reduce(buf[:nparam + 1], group)
-            grads = _split_flat(buf[:nparam], ps)
-            gE = buf[nparam] if ctx.has_energy else None
+            flat, dE = combine_backward(buf, nparam, group)
+            grads = _split_flat(flat, ps)
+            gE = dE if ctx.has_energy else None
         need = ctx.needs_input_grad
         out = [None] * n_in
         if gE is not None and need[9]:

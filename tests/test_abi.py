@@ -1,0 +1,76 @@
+"""CPU tests of the drop-in boundary: libpde_b200.so loads, exports every symbol that
+include/pde_b200.h declares, and its pure (no-GPU) queries answer; the ctypes structures match
+the header's layout.  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import pde_b200 as pb
+from pde_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "pde_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pde_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported():
+    lib = pb.load_library()
+    names = _declared_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pde_b200.h but not exported"
+    assert sorted(L.EXPORTS) == names, "ctypes binding and header disagree on the entry points"
+
+
+def test_pure_queries():
+    lib = pb.load_library()
+    assert lib.pde_abi_version() == 1
+    assert lib.pde_strerror(0) == b"ok"
+    assert b"workspace" in lib.pde_strerror(-3)
+    assert lib.pde_jet_channels(3, 2) == 7 and lib.pde_jet_channels(5, 1) == 6 and lib.pde_jet_channels(2, 0) == 1
+    assert lib.pde_jet_channels(6, 2) < 0
+    assert [lib.pde_program_quantities(k) for k in (1, 2, 3, 4)] == [1, 1, 2, 1]
+    assert [lib.pde_program_order(k) for k in (1, 2, 3, 4)] == [2, 1, 1, 0]
+    assert lib.pde_program_order(99) < 0
+
+
+def test_param_count_and_validation():
+    lib = pb.load_library()
+    net = L.Net()
+    net.dtype, net.dim, net.n_linear, net.activation = L.F32, 3, 5, L.ACT_SIN
+    for i, w in enumerate([3, 64, 64, 64, 64, 1]):
+        net.widths[i] = w
+    n = C.c_int64(0)
+    assert lib.pde_param_count(C.byref(net), C.byref(n)) == 0
+    assert n.value == 12801          # SolutionNet(3, 64, 5): Poisson_ND.py:13-23
+    net.widths[2] = 32               # unequal hidden widths are not a reference shape
+    assert lib.pde_param_count(C.byref(net), C.byref(n)) == -2
+    net.widths[2] = 64
+    net.dim = 9
+    assert lib.pde_param_count(C.byref(net), C.byref(n)) == -2
+
+
+def test_struct_layout_matches_header():
+    # sizes follow from the C declarations (int32 / double / pointer members, natural alignment)
+    assert C.sizeof(L.Net) == 4 * 4 + 9 * 4 + 4 + 8 * 8 + 8 * 8        # 52 -> padded to 56, then 16 pointers
+    assert C.sizeof(L.Envelope) == 4 + 5 * 4 + 2 * 8 + 5 * 8 * 8
+    assert C.sizeof(L.Program) == 8 + 3 * 8 + 3 * 8
+    assert L.Wan.env_u.offset == 8 + 6 * 8 + 3 * 8
+
+
+def test_no_cpu_fallback():
+    """Host tensors are refused loudly; nothing routes through the oracle."""
+    import torch
+    m = pb.poisson.SolutionNet(2, 16, 3)
+    X = torch.rand(8, 2) * 2
+    with pytest.raises(pb.PdeError):
+        pb.poisson.pinn_residual_loss(m, X, torch.ones(8, 1), 2.0)
+    src = open(os.path.join(ROOT, "neural-network-based-pde-solver_b200", "ops.py")).read()
+    src += open(os.path.join(ROOT, "neural-network-based-pde-solver_b200", "poisson.py")).read()
+    assert "oracle" not in src
