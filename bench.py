@@ -282,17 +282,19 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "how": "pinned host X,f -> device on a copy stream one step ahead; loss .item()-style readback every step"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 3 * args.steps,   # per step: tc_pack_kernel, tc_kernel<3,2,sin>, reduce_kernel
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})",
                          "kernel_ms": k_ms, "flop_per_point": FLOP_PER_POINT,
+                         "tensor_pipe_active_pct_ncu": prof.get("tensor_pipe_active_pct"),
+                         "traffic_source": prof.get("source"),
                          "hbm_achieved_gbs": (4 * (DIM + 1) * N) / (k_ms * 1e-3) / 1e9},
         }
         if world == 1 and not args.no_cpu_baseline:
-            rate, dt = cpu_reference_rate(n_chunks=16, threads=os.cpu_count())
+            rate, dt = cpu_reference_rate(n_chunks=64, threads=os.cpu_count())
             out["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
-                                   "sample": f"{16 * CPU_CHUNK} of the 2^22 points in 2^16 chunks ({dt:.1f} s), "
+                                   "sample": f"{64 * CPU_CHUNK} of the 2^22 points (the whole step) in 2^16 chunks ({dt:.1f} s), "
                                              "oracle/autograd_ref.py (the reference's nested-autograd algorithm), fp32"}
         print(json.dumps(out), flush=True)
     if world > 1:
