@@ -681,6 +681,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
             if constexpr (LAP) av[1 + ND][e] = fmaf(s1, z[1 + ND][e], s2 * S);
           }
+          // Operand tile first: its fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) would otherwise also wait
+          // for the stash stores below to be acknowledged by L2.
+          if constexpr (!LAST) {
+            store_chunk(sT1, j, av);
+            chunk_done(j);
+          } else {
+            const float w0v = sWL[u0], w1v = sWL[u0 + 1];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              outacc[0][c] = fmaf(w0v, av[c][0], fmaf(w1v, av[c][1], outacc[0][c]));
+              outacc[1][c] = fmaf(w0v, av[c][2], fmaf(w1v, av[c][3], outacc[1][c]));
+            }
+          }
           if (do_bwd) {
             __stcg(stash_at(l, j, 0), make_float4(sv0[0], sv0[1], sv0[2], sv0[3]));
             __stcg(stash_at(l, j, 1), make_float4(sv1[0], sv1[1], sv1[2], sv1[3]));
@@ -693,17 +706,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             // z has been consumed: fetch the accumulators of the next chunk now
 #pragma unroll
             for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), z[c]);
-          }
-          if constexpr (!LAST) {
-            store_chunk(sT1, j, av);
-            chunk_done(j);
-          } else {
-            const float w0v = sWL[u0], w1v = sWL[u0 + 1];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-              outacc[0][c] = fmaf(w0v, av[c][0], fmaf(w1v, av[c][1], outacc[0][c]));
-              outacc[1][c] = fmaf(w0v, av[c][2], fmaf(w1v, av[c][3], outacc[1][c]));
-            }
           }
         }
         if constexpr (!L0) reg ^= 1;
