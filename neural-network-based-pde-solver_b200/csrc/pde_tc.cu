@@ -22,6 +22,7 @@
 // of the CTA and are written once, as a per-CTA partial vector that reduce_kernel sums in fixed order.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <type_traits>
@@ -60,6 +61,7 @@ struct TcArgs {
   double* psums;                // [grid][8]
   float4* stash;                // [grid][stash_f4]
   long long PP, stash_f4, off_gW0, off_gb0, off_gW, off_gwL, off_gbL;
+  long long* dbg;               // timeline buffer (builds with -DPDE_TC_TIMELINE only), else null
 };
 
 // ---------------------------------------------------------------- per-element math
@@ -231,6 +233,16 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
   asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
+// stash slots are written and later read by the same thread: plain (weak) 128-bit accesses that do
+// not allocate in L1
+__device__ __forceinline__ void stash_st(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 stash_ld(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
 // fire-and-forget fp32 add (round to nearest) to global memory
 __device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -346,6 +358,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   const int tile_begin = (int)(((long long)a.num_tiles * blockIdx.x) / gridDim.x);
   const int tile_end = (int)(((long long)a.num_tiles * (blockIdx.x + 1)) / gridDim.x);
 
+#ifdef PDE_TC_TIMELINE
+  // development timeline: (event id, clock) pairs of CTA 0, epilogue warp 0 and the issuer
+  int dbg_n = 0;
+  auto TS = [&](int id) {
+    if (a.dbg && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == NEPI) && dbg_n < 2000) {
+      long long* p = a.dbg + (warp == 0 ? 0 : 4096) + 2 * dbg_n;
+      p[0] = id; p[1] = clock64();
+      ++dbg_n;
+    }
+  };
+#else
+  auto TS = [](int) {};
+#endif
   // accumulator address of jet channel c in region r: pair c/2 at columns 64 (c/2), lane half c%2
   auto d_addr = [&](int r, int c) { return taddr_of(tmem, 16 * (c & 1), COL_R0 + 192 * r + 64 * (c >> 1)); };
   auto w_addr = [&](int l) { return sWT + (WRES ? (l - 1) * 2 * TILE_BYTES : 0); };
@@ -398,6 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           for (int j = 0; j < 4; ++j) {
             mbar_wait(&bar_chunk[j], ph_chunk);
             tc_fence_after();
+            TS(100 + 10 * l + j);
             if (elect_one()) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
@@ -425,6 +451,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           for (int j = 0; j < 4; ++j) {
             mbar_wait(&bar_chunk[j], ph_chunk);
             tc_fence_after();
+            TS(200 + 10 * l + j);
             // dgrad: Ab_{l-1,c} += Zb_{l,c}[:, K step j] W_l[K step j, :]
             if (elect_one()) {
 #pragma unroll
@@ -600,6 +627,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const long long base = (long long)tile * TP;
+      TS(1);
       // every MMA of the previous tile has completed before X^T / the operand sets are rewritten
       if (w_pending) {
         mbar_wait(bar_w, ph_w);
@@ -634,11 +662,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       // ================= forward =================
       auto fwd_layer = [&](auto l0_tag, auto last_tag, const int l) {
         constexpr bool L0 = decltype(l0_tag)::value, LAST = decltype(last_tag)::value;
+        TS(10 + l);
         if constexpr (!L0) {
           mbar_wait(bar_d, ph_d);
           ph_d ^= 1;
           tc_fence_after();
         }
+        TS(20 + l);
         float z[C][4];   // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]; chunk j+1 is fetched while chunk j is processed
         const uint32_t zsrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
         if constexpr (!L0) {
@@ -661,7 +691,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               if constexpr (LAP) z[1 + ND][e] = 0.f;
             }
           } else {
+            if (l == 1) TS(300 + j);
             tmem_ld_wait();
+            if (l == 1) TS(310 + j);
             const float b0v = sB[l * 64 + u0], b1v = sB[l * 64 + u0 + 1];
             z[0][0] += b0v; z[0][1] += b1v; z[0][2] += b0v; z[0][3] += b1v;
           }
@@ -684,8 +716,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           // Operand tile first: its fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) would otherwise also wait
           // for the stash stores below to be acknowledged by L2.
           if constexpr (!LAST) {
+            if (l == 1) TS(320 + j);
             store_chunk(sT1, j, av);
+            if (l == 1) TS(330 + j);
             chunk_done(j);
+            if (l == 1) TS(340 + j);
           } else {
             const float w0v = sWL[u0], w1v = sWL[u0 + 1];
 #pragma unroll
@@ -745,6 +780,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           for (int c = 0; c < C; ++c) nj[c] = 0.f;
         }
       }
+      TS(2);
       if (!do_bwd) continue;
       if (adj_scale == 0.f) {
         // Power-of-two scale of this CTA's adjoints, from its first tile: the largest network-jet
@@ -803,11 +839,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         };
         load_cur(0);
         load_prv(0);
+        TS(30 + l);
         if constexpr (!TOP) {
           mbar_wait(bar_d, ph_d);   // Ab_l is complete
           ph_d ^= 1;
           tc_fence_after();
         }
+        TS(40 + l);
         float ab[C][4];
         const uint32_t absrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
         if constexpr (!TOP) {
@@ -888,9 +926,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
           if (j == 0 && w_pending) {
             // the previous layer's wgrad still reads both operand sets: wait for it before the first store
+            TS(50 + l);
             mbar_wait(bar_w, ph_w);
             ph_w ^= 1;
             w_pending = false;
+            TS(60 + l);
           }
           store_chunk(sT2, j, zb);
           if constexpr (LK >= 1) {
@@ -1134,6 +1174,30 @@ static int path_override() {
   return !e ? -1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc") == 0 ? 1 : -1));
 }
 
+#ifdef PDE_TC_TIMELINE
+// Development build only (make EXTRA=-DPDE_TC_TIMELINE): PDE_B200_TIMELINE=<file> records (event, clock)
+// pairs of CTA 0 and writes them after the launch (this synchronises the stream).
+static long long* timeline_buffer() {
+  static long long* buf = nullptr;
+  if (!getenv("PDE_B200_TIMELINE")) return nullptr;
+  if (!buf && cudaMalloc(&buf, 8192 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemset(buf, 0, 8192 * sizeof(long long));
+  return buf;
+}
+static void timeline_dump(long long* buf, cudaStream_t st) {
+  if (!buf) return;
+  cudaStreamSynchronize(st);
+  static long long host[8192];
+  cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
+  FILE* f = fopen(getenv("PDE_B200_TIMELINE"), "w");
+  if (!f) return;
+  for (int w = 0; w < 2; ++w)
+    for (int i = 0; i < 2000 && host[w * 4096 + 2 * i] != 0; ++i)
+      fprintf(f, "%d %lld %lld\n", w, host[w * 4096 + 2 * i], host[w * 4096 + 2 * i + 1]);
+  fclose(f);
+}
+#endif
+
 static bool shape_ok(const pde_net* net, int order, long long n) {
   if (!net || net->dtype != PDE_F32) return false;
   if (net->dim < 1 || net->dim > PDE_MAX_DIM) return false;
@@ -1266,7 +1330,13 @@ int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde
   a.partial = partial; a.psums = psums; a.stash = stash;
   a.PP = p.PP; a.stash_f4 = p.stash_f4;
   a.off_gW0 = p.off_gW0; a.off_gb0 = p.off_gb0; a.off_gW = p.off_gW; a.off_gwL = p.off_gwL; a.off_gbL = p.off_gbL;
+#ifdef PDE_TC_TIMELINE
+  a.dbg = timeline_buffer();
+#endif
   if (launch_tc(p, a, st) != cudaSuccess) return PDE_ERR_CUDA;
+#ifdef PDE_TC_TIMELINE
+  timeline_dump(a.dbg, st);
+#endif
 
   ReduceArgs<float> r;
   memset(&r, 0, sizeof(r));

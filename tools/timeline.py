@@ -1,0 +1,40 @@
+"""Development aid (GPU): per-step timeline of CTA 0 (epilogue warp 0 and the MMA issuer).
+Needs a library built with `make -C neural-network-based-pde-solver_b200/csrc EXTRA=-DPDE_TC_TIMELINE`.
+    PDE_B200_TIMELINE=gpurun_out/timeline.txt python tools/timeline.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+out = os.environ.setdefault("PDE_B200_TIMELINE", "gpurun_out/timeline.txt")
+import torch, pde_b200 as pb
+torch.manual_seed(0)
+m = pb.poisson.SolutionNet(3, 64, 5, "FBC").cuda()
+N = 1 << 20
+X = torch.rand(N, 3, device="cuda") * 2
+f = pb.poisson.rhs_f_for_u_sin(X, 2.0, [1, 1, 1])
+for _ in range(2):
+    m.zero_grad()
+    l = pb.poisson.pinn_residual_loss(m, X, f, 2.0); l.backward()
+torch.cuda.synchronize()
+ev = [[], []]
+for line in open(out):
+    w, i, c = line.split()
+    ev[int(w)].append((int(i), int(c)))
+names = {1: "tile start", 2: "program done"}
+for k in range(5):
+    names[10 + k] = f"F{k} enter"; names[20 + k] = f"F{k} D ready"; names[30 + k] = f"B{k} enter"; names[40 + k] = f"B{k} Ab ready"
+    names[50 + k] = f"B{k} want sets"; names[60 + k] = f"B{k} sets free"
+    names[300 + k] = f"  F1 chunk {k} top"; names[310 + k] = f"  F1 chunk {k} tmem ready"; names[320 + k] = f"  F1 chunk {k} math done"
+    names[330 + k] = f"  F1 chunk {k} stsm issued"; names[340 + k] = f"  F1 chunk {k} fenced+arrived"
+e = ev[0]
+starts = [i for i, (id_, _) in enumerate(e) if id_ == 1]
+if len(starts) > 6:
+    a, b = starts[4], starts[5]
+    t0 = e[a][1]
+    print("epilogue warp 0 (cycles since tile start; delta)")
+    prev = t0
+    for id_, c in e[a:b + 1]:
+        print(f"  {names.get(id_, id_):28s} {c - t0:8d}  +{c - prev}")
+        prev = c
+    print("issuer (100+10l+j: fwd chunk j seen, 200+10l+j: dgrad chunk j seen)")
+    for id_, c in ev[1]:
+        if t0 <= c <= e[b][1]:
+            print(f"  {id_:4d} {c - t0:8d}")
