@@ -13,6 +13,7 @@ from ._lib import PdeError, load as load_library
 from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, all_reduce_grads, mlp_jets, residual_means,
                   wan_means)
 from . import poisson
+from . import schrodinger
 
 __all__ = ["PdeError", "load_library", "EnvelopeSpec", "ProgramSpec", "WanSpec", "NO_ENVELOPE", "mlp_jets",
-           "residual_means", "wan_means", "all_reduce_grads", "poisson"]
+           "residual_means", "wan_means", "all_reduce_grads", "poisson", "schrodinger"]

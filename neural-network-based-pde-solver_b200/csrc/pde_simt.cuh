@@ -605,10 +605,10 @@ __global__ void net_kernel(const KArgs<T> a) {
       dred[tid * 5 + 4] = gE;
     }
     __syncthreads();
-    if (tid < 5) {
+    for (int k = tid; k < 5; k += nt) {   // (a CTA can have fewer than 5 threads: tiny batches of narrow nets)
       double v = 0.0;
-      for (int pp = 0; pp < P; ++pp) v += dred[pp * 5 + tid];
-      a.psums[(long long)blockIdx.x * 8 + tid] = v;
+      for (int pp = 0; pp < P; ++pp) v += dred[pp * 5 + k];
+      a.psums[(long long)blockIdx.x * 8 + k] = v;
     }
   }
 }

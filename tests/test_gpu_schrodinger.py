@@ -1,0 +1,164 @@
+"""GPU parity tests of the Schrödinger drop-ins (pde_b200.schrodinger.*) against the golden
+fixtures produced by the live reference scripts (tests/golden/make_golden.py): IPW 1-D PINN / DRM
+(hard-BC and forced-node ansatz), IPW 1-D WAN, QHO 2-D PINN / DRM / WAN, KH 1-D PINN / DRM / WAN with
+trainable energy.  fp64 at 1e-10-level, fp32 at 1e-5-level (BASELINE.json north_star); the WAN and
+quotient losses, whose gradients are differences of gradient vectors, get 4x those bars as in
+tests/test_gpu_poisson.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_grads_close, grads_from, load_golden, net_from
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float64: 2e-10, torch.float32: 1e-5}
+DTYPES = [torch.float64, torch.float32]
+
+
+def _load(net, Ws, bs):
+    lin = [m for m in net if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for l, W, b in zip(lin, Ws, bs):
+            l.weight.copy_(torch.tensor(W)); l.bias.copy_(torch.tensor(b))
+    return lin
+
+
+def _grads(lin):
+    z = lambda p: (p.grad if p.grad is not None else torch.zeros_like(p)).double().cpu().numpy()
+    return [z(l.weight) for l in lin], [z(l.bias) for l in lin]
+
+
+def _zero(*mods):
+    for m in mods:
+        for p in m.parameters():
+            p.grad = None
+
+
+def _close(a, b, tol):
+    a = float(a.detach()) if torch.is_tensor(a) else float(a)
+    assert abs(a - float(b)) <= tol * max(abs(float(b)), 1e-3), (a, float(b))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name", ["ipw1d_fbc_n2", "ipw1d_fn_n3"])
+def test_ipw1d_pinn_drm(name, dtype):
+    from pde_b200.schrodinger import ipw_1d_pinn_drm as I
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    L, n = float(g["L"]), int(g["n"])
+    kw = dict(FN=True, num_states=3) if name.endswith("fn_n3") else dict(enforce_bc=True)
+    model = I.FCN([1, 20, 20, 1], L=L, **kw).double()
+    lin = _load(model.net, Ws, bs)
+    model = model.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = TOL[dtype]
+    lp = I.PINN_loss(model, x, n, L); lp.backward()
+    _close(lp, g["pinn_loss"], tol)
+    assert_grads_close(_grads(lin), grads_from(g, "pinn_"), tol, name + " pinn")
+    _zero(model)
+    ld = I.DRM_loss(model, x); ld.backward()
+    _close(ld, g["drm_loss"], tol)
+    assert_grads_close(_grads(lin), grads_from(g, "drm_"), 4 * tol, name + " drm")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ipw1d_wan(dtype):
+    from pde_b200.schrodinger import ipw_1d_wan as W
+    g = load_golden("ipw1d_wan_n2")
+    L, n = float(g["L"]), int(g["n"])
+    um = W.FCN([1, 20, 20, 1], L=L, enforce_bc=True).double()
+    vm = W.FCN([1, 10, 10, 1], L=L, enforce_bc=False).double()
+    ul = _load(um.net, *net_from(g, "u_")); vl = _load(vm.net, *net_from(g, "v_"))
+    um, vm = um.to("cuda", dtype), vm.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = 4 * TOL[dtype]
+    total, lv, lpde, lnorm = W.WAN_loss(um, vm, x, n, L, 1.0, 1.0)
+    for got, key in ((total, "total"), (lv, "loss_v"), (lpde, "loss_pde"), (lnorm, "loss_norm")):
+        _close(got, g[key], tol)
+    total.backward(retain_graph=True)
+    assert_grads_close(_grads(ul), grads_from(g, "tot_u_"), tol, "tot/u")
+    assert_grads_close(_grads(vl), grads_from(g, "tot_v_"), tol, "tot/v")
+    _zero(um, vm)
+    lv.backward()
+    assert_grads_close(_grads(ul), grads_from(g, "lv_u_"), tol, "lv/u")
+    assert_grads_close(_grads(vl), grads_from(g, "lv_v_"), tol, "lv/v")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name,tech", [("qho2d_fbc_00", "FBC"), ("qho2d_fn_21", "FN")])
+def test_qho2d_pinn_drm(name, tech, dtype):
+    from pde_b200.schrodinger import qho_2d as Q
+    g = load_golden(name)
+    L, nx, ny, E = float(g["L"]), int(g["nx"]), int(g["ny"]), float(g["E"])
+    model = Q.FCN([2, 16, 16, 16, 1], nx, ny, tech).double()
+    np.testing.assert_allclose(model.nodes_x.double().numpy(), g["nodes_x"], rtol=0, atol=0)
+    lin = _load(model.net, *net_from(g))
+    model = model.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    y = torch.tensor(g["y"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = TOL[dtype]
+    lp = Q.PINN_loss(model, x, y, E, L); lp.backward()
+    _close(lp, g["pinn_loss"], tol)
+    assert_grads_close(_grads(lin), grads_from(g, "pinn_"), tol, name + " pinn")
+    _zero(model)
+    ld = Q.DRM_loss(model, x, y, L); ld.backward()
+    _close(ld, g["drm_loss"], tol)
+    assert_grads_close(_grads(lin), grads_from(g, "drm_"), 4 * tol, name + " drm")
+    with pytest.raises(ValueError):
+        model.technique = "XX"
+        Q.PINN_loss(model, x, y, E, L)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_qho2d_wan(dtype):
+    from pde_b200.schrodinger import qho_2d as Q
+    g = load_golden("qho2d_wan_10")
+    L, nx, ny = float(g["L"]), int(g["nx"]), int(g["ny"])
+    um = Q.FCN([2, 16, 16, 1], nx, ny, "FBC").double()
+    vm = Q.FCN([2, 10, 10, 1], nx, ny, "FBC").double()
+    ul = _load(um.net, *net_from(g, "u_")); vl = _load(vm.net, *net_from(g, "v_"))
+    um, vm = um.to("cuda", dtype), vm.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    y = torch.tensor(g["y"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = 4 * TOL[dtype]
+    total, lv, lpde, lnorm = Q.WAN_loss(um, vm, x, y, nx, ny, L, 1.0, 1.0)
+    for got, key in ((total, "total"), (lv, "loss_v"), (lpde, "loss_pde"), (lnorm, "loss_norm")):
+        _close(got, g[key], 10 * tol)     # (4 L^2 mean u^2 - 1)^2 amplifies the rounding of mean u^2
+    total.backward(retain_graph=True)
+    assert_grads_close(_grads(ul), grads_from(g, "tot_u_"), 10 * tol, "tot/u")
+    assert_grads_close(_grads(vl), grads_from(g, "tot_v_"), 10 * tol, "tot/v")
+    _zero(um, vm)
+    lv.backward()
+    assert_grads_close(_grads(ul), grads_from(g, "lv_u_"), 10 * tol, "lv/u")
+    assert_grads_close(_grads(vl), grads_from(g, "lv_v_"), 10 * tol, "lv/v")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name,tech", [("kh1d_raw", "RAW"), ("kh1d_fbc", "FBC")])
+def test_kh1d(name, tech, dtype):
+    from pde_b200.schrodinger import kh_1d as K
+    g = load_golden(name)
+    L, alpha, V0 = float(g["L"]), 2.0, -24.856
+    model = K.UnifiedEigenModel([1, 16, 16, 1], technique=tech, E_init=float(g["E"])).double()
+    vm = K.FCN1D([1, 10, 10, 1], technique="RAW").double()
+    ul = _load(model.u_model.net, *net_from(g, "u_")); vl = _load(vm.net, *net_from(g, "v_"))
+    model, vm = model.to("cuda", dtype), vm.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    Vx = K.V_KH(x.detach(), alpha=alpha, V0=V0)
+    assert np.max(np.abs(Vx.double().cpu().numpy() - g["V"])) <= (1e-11 if dtype == torch.float64 else 2e-5)
+    tol = TOL[dtype] if dtype == torch.float64 else 4 * TOL[dtype]   # fp32: V itself is rounded (n_theta mean)
+    lp = K.pinn_loss(model, x, alpha, V0); lp.backward()
+    _close(lp, g["pinn_loss"], tol)
+    assert_grads_close(_grads(ul), grads_from(g, "pinn_"), tol, name + " pinn")
+    _close(model.energy.grad, g["pinn_gE"], tol)
+    _zero(model, vm)
+    ld = K.drm_loss(model, x, alpha, V0, L); ld.backward()
+    _close(ld, g["drm_loss"], tol)
+    assert_grads_close(_grads(ul), grads_from(g, "drm_"), 4 * tol, name + " drm")
+    _zero(model, vm)
+    lw, ln = K.wan_loss(model, vm, x, alpha, V0, L)
+    _close(lw, g["wan_pde"], 10 * tol); _close(ln, g["wan_norm"], 10 * tol)
+    (lw + ln).backward()
+    assert_grads_close(_grads(ul), grads_from(g, "wan_u_"), 10 * tol, name + " wan/u")
+    assert_grads_close(_grads(vl), grads_from(g, "wan_v_"), 10 * tol, name + " wan/v")
+    _close(model.energy.grad, g["wan_gE"], 10 * tol)
