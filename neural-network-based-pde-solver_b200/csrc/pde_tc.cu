@@ -561,15 +561,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     float adj_scale = 0.f;   // power-of-two scale of the adjoints of this CTA (0 = not chosen yet)
 
     // write 4 values (2 rows x 2 adjacent units) of every channel of chunk j into an operand set
-    auto store_chunk = [&](uint32_t set, int j, const float (&v)[C][4]) {
-      const uint32_t addr = set + sm_base + ((((2 * j + h) ^ sm_r7) & 7) << 4);
+    auto pack_chunk = [&](const float (&v)[C][4], uint32_t (&pk)[C][4]) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        uint32_t h0, l0, h1, l1;
-        split2(v[c][0], v[c][1], h0, l0);
-        split2(v[c][2], v[c][3], h1, l1);
-        stsm_x4(addr + c * 2 * TILE_BYTES, h0, h1, l0, l1);
+        split2(v[c][0], v[c][1], pk[c][0], pk[c][2]);
+        split2(v[c][2], v[c][3], pk[c][1], pk[c][3]);
       }
+    };
+    auto put_chunk = [&](uint32_t set, int j, const uint32_t (&pk)[C][4]) {
+      const uint32_t addr = set + sm_base + ((((2 * j + h) ^ sm_r7) & 7) << 4);
+#pragma unroll
+      for (int c = 0; c < C; ++c) stsm_x4(addr + c * 2 * TILE_BYTES, pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+    };
+    auto store_chunk = [&](uint32_t set, int j, const float (&v)[C][4]) {
+      uint32_t pk[C][4];
+      pack_chunk(v, pk);
+      put_chunk(set, j, pk);
     };
     auto chunk_done = [&](int j) {
       fence_proxy_async();
@@ -924,52 +931,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
             load_cur(j + 1);
           }
+          uint32_t zk[C][4];
+          pack_chunk(zb, zk);
+          float ap[C][4];
+          if constexpr (LK >= 1) {
+            // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
+            const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
+            float zp[C][4];
+            if constexpr (LK >= 2) {
+#pragma unroll
+              for (int c = 1; c < C; ++c) {
+                zp[c][0] = prv[1 + c].x; zp[c][1] = prv[1 + c].y; zp[c][2] = prv[1 + c].z; zp[c][3] = prv[1 + c].w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int u = u0 + (e & 1);
+#pragma unroll
+                for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
+                if constexpr (LAP) zp[1 + ND][e] = 0.f;
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float s0, s1, s2, s3;
+              act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
+              ap[0][e] = s0;
+              float S = 0.f;
+#pragma unroll
+              for (int i = 0; i < ND; ++i) {
+                ap[1 + i][e] = s1 * zp[1 + i][e];
+                S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
+              }
+              if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
+            }
+            if (j < 3) load_prv(j + 1);
+          }
           if (j == 0 && w_pending) {
-            // the previous layer's wgrad still reads both operand sets: wait for it before the first store
+            // the previous layer's wgrad still reads both operand sets: both results of chunk 0 are
+            // computed before waiting for it, the stores come after
             TS(50 + l);
             mbar_wait(bar_w, ph_w);
             ph_w ^= 1;
             w_pending = false;
             TS(60 + l);
           }
-          store_chunk(sT2, j, zb);
-          if constexpr (LK >= 1) {
-            // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
-            float ap[C][4];
-            {
-              const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
-              float zp[C][4];
-              if constexpr (LK >= 2) {
-#pragma unroll
-                for (int c = 1; c < C; ++c) {
-                  zp[c][0] = prv[1 + c].x; zp[c][1] = prv[1 + c].y; zp[c][2] = prv[1 + c].z; zp[c][3] = prv[1 + c].w;
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int u = u0 + (e & 1);
-#pragma unroll
-                  for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
-                  if constexpr (LAP) zp[1 + ND][e] = 0.f;
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float s0, s1, s2, s3;
-                act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
-                ap[0][e] = s0;
-                float S = 0.f;
-#pragma unroll
-                for (int i = 0; i < ND; ++i) {
-                  ap[1 + i][e] = s1 * zp[1 + i][e];
-                  S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
-                }
-                if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
-              }
-            }
-            if (j < 3) load_prv(j + 1);
-            store_chunk(sT1, j, ap);
-          }
+          put_chunk(sT2, j, zk);
+          if constexpr (LK >= 1) store_chunk(sT1, j, ap);
           chunk_done(j);
         }
         if constexpr (!TOP) reg ^= 1;
