@@ -20,7 +20,8 @@ typedef __nv_bfloat16 op_t;
 using namespace pde::tc;
 
 // modes: 0 A K-major, B K-major | 1 A K-major, B MN-major | 2 A MN-major, B MN-major
-//        3 = mode 0 but D at lane offset 16, column 64 | 4 = N=8 K-major B | 5 = x2 ordering (mode 0)
+//        3 = mode 0 but D at lane offset 16, column 64 | 4 = N=8 K-major B
+//        5 = A MN-major, B MN-major N=16 slice at column offset 32 of the B tile (wgrad^T chunk)
 struct Args {
   const float* A;  // [64][64] logical "row-major as stored in the tile"
   const float* B;  // [64][64]
@@ -54,16 +55,16 @@ __global__ void __launch_bounds__(128, 1) probe(Args a) {
   const uint32_t tb = tmem_base_s;
 
   // zero the TMEM region we will read raw (so garbage is visible as such): skip, just run MMA
-  const int N = (a.mode == 4) ? 8 : 64;
+  const int N = (a.mode == 4) ? 8 : (a.mode == 5 ? 16 : 64);
   const int lane_off = (a.mode == 3) ? 16 : 0;
   const int col_off = (a.mode == 3) ? 64 : 0;
   if (tid == 0) {
-    const bool a_mn = (a.mode == 2), b_mn = (a.mode == 1 || a.mode == 2);
+    const bool a_mn = (a.mode == 2 || a.mode == 5), b_mn = (a.mode == 1 || a.mode == 2 || a.mode == 5);
     const uint32_t idesc = make_idesc(64, N, a_mn, b_mn);
     const uint32_t d = taddr_of(tb, lane_off, col_off);
     for (int ks = 0; ks < 4; ++ks) {
       uint64_t ad = a_mn ? desc_mnmajor(smem_u32(tA), ks) : desc_kmajor(smem_u32(tA), ks);
-      uint64_t bd = b_mn ? desc_mnmajor(smem_u32(tB), ks) : desc_kmajor(smem_u32(tB), ks);
+      uint64_t bd = b_mn ? desc_mnmajor(smem_u32(tB) + (a.mode == 5 ? 64 : 0), ks) : desc_kmajor(smem_u32(tB), ks);
       mma_bf16(d, ad, bd, idesc, ks > 0);
     }
     mma_commit(&bar);
@@ -110,7 +111,7 @@ int main() {
   cudaMemcpy(dB, B.data(), 16384, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES + 1024);
   int fails = 0;
-  for (int mode = 0; mode <= 4; ++mode) {
+  for (int mode = 0; mode <= 5; ++mode) {
     cudaMemset(dD, 0, 16384); cudaMemset(dR, 0, 32768);
     Args a{dA, dB, dD, dR, mode};
     probe<<<1, 128, 2 * TILE_BYTES + 1024>>>(a);
@@ -119,15 +120,15 @@ int main() {
     std::vector<float> D(4096), R(8192);
     cudaMemcpy(D.data(), dD, 16384, cudaMemcpyDeviceToHost);
     cudaMemcpy(R.data(), dR, 32768, cudaMemcpyDeviceToHost);
-    const int N = mode == 4 ? 8 : 64;
+    const int N = mode == 4 ? 8 : (mode == 5 ? 16 : 64);
     double maxerr = 0, maxref = 0;
     std::vector<double> ref(64 * 64, 0.0);
     for (int m = 0; m < 64; ++m)
       for (int n = 0; n < N; ++n) {
         double s = 0;
         for (int k = 0; k < 64; ++k) {
-          double av = (mode == 2) ? bf(A[k * 64 + m]) : bf(A[m * 64 + k]);
-          double bv = (mode == 1 || mode == 2) ? bf(B[k * 64 + n]) : bf(B[n * 64 + k]);
+          double av = (mode == 2 || mode == 5) ? bf(A[k * 64 + m]) : bf(A[m * 64 + k]);
+          double bv = (mode == 5) ? bf(B[k * 64 + 32 + n]) : ((mode == 1 || mode == 2) ? bf(B[k * 64 + n]) : bf(B[n * 64 + k]));
           s += av * bv;
         }
         ref[m * 64 + n] = s;
