@@ -1,5 +1,5 @@
 // pde_tc.cu — Blackwell tensor-core (tcgen05 / TMEM) fused collocation loss step, fp32 parity
-// through 3-term bf16 operand splits (x = hi + lo; hi*hi + lo*hi + hi*lo, fp32 accumulate).
+// through 3-term fp16 operand splits (x = hi + lo; hi*hi + lo*hi + hi*lo, fp32 accumulate).
 //
 // What it computes is the reference's nested-autograd step (Poisson_Equations/Poisson_ND.py:61-71
 // grad / Laplacian, :91-103 PINN / Deep-Ritz losses, :240 loss.backward()) for networks
@@ -104,15 +104,6 @@ __device__ __forceinline__ void act_eval(int act, float z, bool big, float& v0, 
   } else {
     v0 = tanhf(z); v1 = 1.f - v0 * v0;
   }
-}
-
-// write the (hi, lo) bf16 pairs of two adjacent units of one row into channel c of a tile set
-__device__ __forceinline__ void store_pair(unsigned char* set, int c, int row, int u0, float x0, float x1) {
-  uint32_t hi, lo;
-  split2(x0, x1, hi, lo);
-  const uint32_t off = tile_off(row, u0 >> 3) + ((u0 & 7) << 1);
-  *reinterpret_cast<uint32_t*>(set + (2 * c) * TILE_BYTES + off) = hi;
-  *reinterpret_cast<uint32_t*>(set + (2 * c + 1) * TILE_BYTES + off) = lo;
 }
 
 // ---------------------------------------------------------------- envelope + residual program on (value, grad, Lap) jets
@@ -233,18 +224,6 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
   asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
-// stash slots are written and later read by the same thread: plain (weak) 128-bit accesses that do
-// not allocate in L1
-__device__ __forceinline__ void stash_st(float4* p, float4 v) {
-  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float4 stash_ld(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-// fire-and-forget fp32 add (round to nearest) to global memory
-__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // UMMA descriptors as "constant high word + 14-bit start address (16-byte units) in the low word":
