@@ -814,8 +814,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int v = 2; v < NV; ++v) cur[v] = __ldcg(stash_at(l, j, v));
           }
         };
+        // at the top layer A_{n_h-2} is still in T1 from the forward sweep: nothing to rebuild
+        constexpr bool REFILL = (LK >= 1) && !TOP;
         auto load_prv = [&](int j) {
-          if constexpr (LK >= 1) {
+          if constexpr (REFILL) {
             prv[0] = __ldcg(stash_at(l - 1, j, 0)); prv[1] = __ldcg(stash_at(l - 1, j, 1));
             if constexpr (LK >= 2) {
 #pragma unroll
@@ -913,7 +915,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           uint32_t zk[C][4];
           pack_chunk(zb, zk);
           float ap[C][4];
-          if constexpr (LK >= 1) {
+          if constexpr (REFILL) {
             // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
             const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
             float zp[C][4];
@@ -956,7 +958,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             TS(60 + l);
           }
           put_chunk(sT2, j, zk);
-          if constexpr (LK >= 1) store_chunk(sT1, j, ap);
+          if constexpr (REFILL) store_chunk(sT1, j, ap);
           chunk_done(j);
         }
         if constexpr (!TOP) reg ^= 1;
