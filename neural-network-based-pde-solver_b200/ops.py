@@ -41,10 +41,16 @@ def _linear_stack(model: nn.Module):
     seq = model
     if hasattr(model, "u_model"):
         seq = model.u_model
-    if hasattr(seq, "net"):
-        seq = seq.net
-    elif hasattr(seq, "layers"):
-        seq = seq.layers
+    holder = seq   # the module that owns the activation attribute when the stack is a bare ModuleList
+    for _ in range(3):   # FCN_Single.net -> FCN.layers (QHO_1D_PINN_DRM.py:85,64)
+        if isinstance(seq, (nn.Sequential, nn.ModuleList)):
+            break
+        if hasattr(seq, "net"):
+            holder = seq = seq.net
+        elif hasattr(seq, "layers"):
+            holder, seq = seq, seq.layers
+        else:
+            break
     mods = list(seq)
     linears = [m for m in mods if isinstance(m, nn.Linear)]
     others = [m for m in mods if not isinstance(m, nn.Linear)]
@@ -60,7 +66,7 @@ def _linear_stack(model: nn.Module):
             raise NotImplementedError("mixed activations are not supported")
         act = a
     if act is None:  # ModuleList of Linear only: activation kept as an attribute
-        a = getattr(model, "activation", None)
+        a = getattr(holder, "activation", getattr(model, "activation", None))
         name = (type(a).__name__ if a is not None else "sin").lower()
         act = "tanh" if "tanh" in name else "sin"
     return linears, act

@@ -287,6 +287,148 @@ def kh_cases(K):
              **params_np(model.u_model.net, "u_"), **params_np(vm.net, "v_"), **out)
 
 
+# ------------------------------------------------------------------ remaining Schrödinger scripts
+def perturb_biases(*seqs):
+    with torch.no_grad():
+        for seq in seqs:
+            for m in seq:
+                if isinstance(m, torch.nn.Linear):
+                    m.bias.uniform_(-0.3, 0.3)
+
+
+def qho1d_cases(Q1, QW):
+    """QHO_1D_PINN_DRM.py (ModuleList sine network, exp-window / forced nodes) and QHO_1D_WAN.py
+    (tanh networks, trainable energies)."""
+    X_max = 6.0
+    for tag, n, kw in (("qho1d_bc_n1", 1, dict(enforce_bc=True)), ("qho1d_fn_n2", 2, dict(enforce_bc=True, FN=True)),
+                       ("qho1d_fnonly_n3", 3, dict(enforce_bc=False, FN=True))):
+        torch.manual_seed(600 + n)
+        model = Q1.FCN_Single([1, 20, 20, 1], num_states=n, domain_length=2 * X_max, **kw).double()
+        x = torch.linspace(-X_max, X_max, 81, dtype=torch.float64).view(-1, 1).requires_grad_(True)
+        out = {}
+        for nm, fn in (("pinn", lambda: Q1.PINN_loss(model, x)), ("drm", lambda: Q1.DRM_loss(model, x)),
+                       ("norm", lambda: Q1.normalization_loss(model, x)),
+                       ("orth", lambda: Q1.Orthogonal_loss(model, x, n, X_max))):
+            zero_grads(model)
+            l = fn()
+            l.backward()
+            out[nm + "_loss"] = np.float64(l.item())
+            out.update(grads_np(model.net.layers, nm + "_"))
+        save(tag, x=x.detach().numpy(), X_max=np.float64(X_max), n=np.int64(n), **params_np(model.net.layers, ""), **out)
+
+    torch.manual_seed(620)
+    L, n = 6.0, 1
+    um = QW.FCN([1, 20, 20, 1], num_states=n, L=L, enforce_bc=True).double()
+    vm = QW.FCN([1, 10, 10, 1], num_states=n, L=L, enforce_bc=False).double()
+    perturb_biases(um.net, vm.net)
+    with torch.no_grad():
+        um.energies.add_(0.1)
+    x = torch.linspace(-L, L, 81, dtype=torch.float64).view(-1, 1).requires_grad_(True)
+    out = {}
+    zero_grads(um, vm)
+    total, lv, lpde, lnorm = QW.WAN_loss(um, vm, x, n, L, 1.0, 1.0)
+    total.backward(retain_graph=True)
+    out.update({"tot_" + k: v for k, v in grads_np(um.net, "u_").items()})
+    out.update({"tot_" + k: v for k, v in grads_np(vm.net, "v_").items()})
+    out["tot_gE"] = um.energies.grad.numpy().copy()
+    zero_grads(um, vm)
+    lv.backward()
+    out.update({"lv_" + k: v for k, v in grads_np(um.net, "u_").items()})
+    out.update({"lv_" + k: v for k, v in grads_np(vm.net, "v_").items()})
+    out["lv_gE"] = um.energies.grad.numpy().copy()
+    save("qho1d_wan_n1", x=x.detach().numpy(), L=np.float64(L), n=np.int64(n), E=np.float64(um.energies.item()),
+         total=np.float64(total.item()), loss_v=np.float64(lv.item()), loss_pde=np.float64(lpde.item()),
+         loss_norm=np.float64(lnorm.item()), **params_np(um.net, "u_"), **params_np(vm.net, "v_"), **out)
+
+
+def ipw_fn_wan_case(WF):
+    """IPW_1D_WAN_FN.py: forced-node ansatz on both networks."""
+    torch.manual_seed(630)
+    L, n = 2.0, 3
+    um = WF.FCN([1, 20, 20, 1], num_states=n, L=L).double()
+    vm = WF.FCN([1, 10, 10, 1], num_states=1, L=L).double()
+    perturb_biases(um.net, vm.net)
+    x = torch.linspace(0.0, L, 65, dtype=torch.float64).view(-1, 1).requires_grad_(True)
+    out = {}
+    zero_grads(um, vm)
+    total, lv, lpde, lnorm = WF.WAN_loss(um, vm, x, n, L, 1.0, 1.0)
+    total.backward(retain_graph=True)
+    out.update({"tot_" + k: v for k, v in grads_np(um.net, "u_").items()})
+    out.update({"tot_" + k: v for k, v in grads_np(vm.net, "v_").items()})
+    zero_grads(um, vm)
+    lv.backward()
+    out.update({"lv_" + k: v for k, v in grads_np(um.net, "u_").items()})
+    out.update({"lv_" + k: v for k, v in grads_np(vm.net, "v_").items()})
+    save("ipw1d_wanfn_n3", x=x.detach().numpy(), L=np.float64(L), n=np.int64(n), total=np.float64(total.item()),
+         loss_v=np.float64(lv.item()), loss_pde=np.float64(lpde.item()), loss_norm=np.float64(lnorm.item()),
+         **params_np(um.net, "u_"), **params_np(vm.net, "v_"), **out)
+
+
+def ipw2d_cases(I2):
+    """IPW_2D.py: the inline PINN / DRM blocks of train_pinn_seperate (:195-228) restated around the
+    imported FCN, plus orthogonal_loss (:113-126)."""
+    L = 2.0
+    for tag, tech, nx, ny in (("ipw2d_fbc_11", "FBC", 1, 1), ("ipw2d_fn_32", "FN", 3, 2)):
+        torch.manual_seed(640 + nx)
+        model = I2.FCN([2, 16, 16, 16, 1], nx, ny, tech).double()
+        g1 = torch.linspace(0.0, L, 12, dtype=torch.float64)
+        xg, yg = torch.meshgrid(g1, g1, indexing="ij")
+        x = xg.clone().requires_grad_(True)
+        y = yg.clone().requires_grad_(True)
+        k2 = (2 * ((nx * np.pi) ** 2 / (2 * L ** 2) + (ny * np.pi) ** 2 / (2 * L ** 2)))
+
+        def jets():
+            u = model(x, y)
+            ux = torch.autograd.grad(u, x, torch.ones_like(u), create_graph=True)[0]
+            uy = torch.autograd.grad(u, y, torch.ones_like(u), create_graph=True)[0]
+            return u, ux, uy
+        zero_grads(model)
+        u, ux, uy = jets()
+        uxx = torch.autograd.grad(ux, x, torch.ones_like(ux), create_graph=True)[0]
+        uyy = torch.autograd.grad(uy, y, torch.ones_like(uy), create_graph=True)[0]
+        lp = torch.mean((uxx + uyy + k2 * u) ** 2)
+        lp.backward()
+        gp = grads_np(model.net, "pinn_")
+        zero_grads(model)
+        u, ux, uy = jets()
+        ld = torch.mean(ux ** 2 + uy ** 2) / torch.mean(u ** 2 + 1e-8)
+        ld.backward()
+        gd = grads_np(model.net, "drm_")
+        zero_grads(model)
+        lo = I2.orthogonal_loss(model, x, y, nx, ny, L)
+        go = {}
+        if torch.is_tensor(lo) and lo.requires_grad:
+            lo.backward()
+            go = grads_np(model.net, "orth_")
+        save(tag, x=x.detach().numpy(), y=y.detach().numpy(), L=np.float64(L), nx=np.int64(nx), ny=np.int64(ny),
+             pinn_loss=np.float64(lp.item()), drm_loss=np.float64(ld.item()), orth_loss=np.float64(float(lo)),
+             u=u.detach().numpy(), **params_np(model.net, ""), **gp, **gd, **go)
+
+
+def qho2d_energy_case(QE):
+    """QHO_2D_Energy.py: PINN residual with the trainable energy E_train (:287-291,382-383)."""
+    L, nx, ny = 6.0, 1, 1
+    torch.manual_seed(650)
+    model = QE.FCN([2, 16, 16, 16, 1], nx, ny, "FBC").double()
+    E_train = torch.nn.Parameter(torch.tensor(QE.Exact_energy(nx, ny, L) + 0.05, dtype=torch.float64))
+    g1 = torch.linspace(-L, L, 12, dtype=torch.float64)
+    xg, yg = torch.meshgrid(g1, g1, indexing="ij")
+    x = xg.clone().requires_grad_(True)
+    y = yg.clone().requires_grad_(True)
+    u = model(x, y)
+    ux = torch.autograd.grad(u, x, torch.ones_like(u), create_graph=True)[0]
+    uy = torch.autograd.grad(u, y, torch.ones_like(u), create_graph=True)[0]
+    uxx = torch.autograd.grad(ux, x, torch.ones_like(ux), create_graph=True)[0]
+    uyy = torch.autograd.grad(uy, y, torch.ones_like(uy), create_graph=True)[0]
+    V = 0.5 * math.sqrt(2) ** 2 * (x ** 2 + y ** 2)
+    lp = torch.mean((-0.5 * (uxx + uyy) + V * u - E_train * u) ** 2)
+    zero_grads(model)
+    lp.backward()
+    save("qho2d_energy_11", x=x.detach().numpy(), y=y.detach().numpy(), L=np.float64(L), nx=np.int64(nx), ny=np.int64(ny),
+         E=np.float64(E_train.item()), pinn_loss=np.float64(lp.item()), pinn_gE=E_train.grad.numpy().copy(),
+         **params_np(model.net, ""), **grads_np(model.net, "pinn_"))
+
+
 def main():
     torch.set_default_dtype(torch.float32)
     P = load_ref("Poisson_Equations/Poisson_ND.py", "ref_poisson_nd")
@@ -298,7 +440,22 @@ def main():
     qho2d_cases(Q)
     K = load_ref("Schrodinger_Equations/Kramers_Henneberger/KH_1D.py", "ref_kh1d")
     kh_cases(K)
+    more()
+
+
+def more():
+    """The scripts added after the first fixture set (run alone with ``make_golden.py more``)."""
+    torch.set_default_dtype(torch.float32)
+    Q1 = load_ref("Schrodinger_Equations/Quantum_Harmonic_Oscillator/QHO_1D_PINN_DRM.py", "ref_qho1d_pd")
+    QW = load_ref("Schrodinger_Equations/Quantum_Harmonic_Oscillator/QHO_1D_WAN.py", "ref_qho1d_wan")
+    qho1d_cases(Q1, QW)
+    WF = load_ref("Schrodinger_Equations/Infinite_Potential_Well/IPW_1D_WAN_FN.py", "ref_ipw_wanfn")
+    ipw_fn_wan_case(WF)
+    I2 = load_ref("Schrodinger_Equations/Infinite_Potential_Well/IPW_2D.py", "ref_ipw2d")
+    ipw2d_cases(I2)
+    QE = load_ref("Schrodinger_Equations/Quantum_Harmonic_Oscillator/QHO_2D_Energy.py", "ref_qho2d_energy")
+    qho2d_energy_case(QE)
 
 
 if __name__ == "__main__":
-    main()
+    more() if sys.argv[1:] == ["more"] else main()

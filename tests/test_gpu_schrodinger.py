@@ -162,3 +162,126 @@ def test_kh1d(name, tech, dtype):
     assert_grads_close(_grads(ul), grads_from(g, "wan_u_"), 10 * tol, name + " wan/u")
     assert_grads_close(_grads(vl), grads_from(g, "wan_v_"), 10 * tol, name + " wan/v")
     _close(model.energy.grad, g["wan_gE"], 10 * tol)
+
+
+# ---------------------------------------------------------------- second fixture set: the remaining scripts
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name,kw", [("qho1d_bc_n1", dict(enforce_bc=True)), ("qho1d_fn_n2", dict(enforce_bc=True, FN=True)),
+                                     ("qho1d_fnonly_n3", dict(enforce_bc=False, FN=True))])
+def test_qho1d_pinn_drm(name, kw, dtype):
+    """QHO_1D_PINN_DRM.py: ModuleList sine network; PINN, DRM, normalisation and orthogonality terms."""
+    from pde_b200.schrodinger import qho_1d_pinn_drm as Q
+    g = load_golden(name)
+    X_max, n = float(g["X_max"]), int(g["n"])
+    model = Q.FCN_Single([1, 20, 20, 1], num_states=n, domain_length=2 * X_max, **kw).double()
+    lin = _load(model.net.layers, *net_from(g))
+    model = model.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = TOL[dtype]
+    for nm, fn, k in (("pinn", lambda: Q.PINN_loss(model, x), 1), ("drm", lambda: Q.DRM_loss(model, x), 4),
+                      ("norm", lambda: Q.normalization_loss(model, x), 4),
+                      ("orth", lambda: Q.Orthogonal_loss(model, x, n, X_max), 4)):
+        _zero(model)
+        l = fn(); l.backward()
+        _close(l, g[nm + "_loss"], k * tol)
+        assert_grads_close(_grads(lin), grads_from(g, nm + "_"), k * tol, f"{name} {nm}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_qho1d_wan(dtype):
+    """QHO_1D_WAN.py: trainable ``energies`` gets its gradient from the same launches."""
+    from pde_b200.schrodinger import qho_1d_wan as W
+    g = load_golden("qho1d_wan_n1")
+    L, n = float(g["L"]), int(g["n"])
+    um = W.FCN([1, 20, 20, 1], num_states=n, L=L, enforce_bc=True).double()
+    vm = W.FCN([1, 10, 10, 1], num_states=n, L=L, enforce_bc=False).double()
+    ul = _load(um.net, *net_from(g, "u_")); vl = _load(vm.net, *net_from(g, "v_"))
+    with torch.no_grad():
+        um.energies.fill_(float(g["E"]))
+    um, vm = um.to("cuda", dtype), vm.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = 10 * 4 * TOL[dtype]
+    total, lv, lpde, lnorm = W.WAN_loss(um, vm, x, n, L, 1.0, 1.0)
+    for got, key in ((total, "total"), (lv, "loss_v"), (lpde, "loss_pde"), (lnorm, "loss_norm")):
+        _close(got, g[key], tol)
+    total.backward(retain_graph=True)
+    assert_grads_close(_grads(ul), grads_from(g, "tot_u_"), tol, "tot/u")
+    assert_grads_close(_grads(vl), grads_from(g, "tot_v_"), tol, "tot/v")
+    _close(um.energies.grad, g["tot_gE"], tol)
+    _zero(um, vm)
+    lv.backward()
+    assert_grads_close(_grads(ul), grads_from(g, "lv_u_"), tol, "lv/u")
+    assert_grads_close(_grads(vl), grads_from(g, "lv_v_"), tol, "lv/v")
+    _close(um.energies.grad, g["lv_gE"], tol)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ipw1d_wan_fn(dtype):
+    from pde_b200.schrodinger import ipw_1d_wan_fn as W
+    g = load_golden("ipw1d_wanfn_n3")
+    L, n = float(g["L"]), int(g["n"])
+    um = W.FCN([1, 20, 20, 1], num_states=n, L=L).double()
+    vm = W.FCN([1, 10, 10, 1], num_states=1, L=L).double()
+    ul = _load(um.net, *net_from(g, "u_")); vl = _load(vm.net, *net_from(g, "v_"))
+    um, vm = um.to("cuda", dtype), vm.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = 4 * TOL[dtype]
+    total, lv, lpde, lnorm = W.WAN_loss(um, vm, x, n, L, 1.0, 1.0)
+    for got, key in ((total, "total"), (lv, "loss_v"), (lpde, "loss_pde"), (lnorm, "loss_norm")):
+        _close(got, g[key], tol)
+    total.backward(retain_graph=True)
+    assert_grads_close(_grads(ul), grads_from(g, "tot_u_"), tol, "tot/u")
+    assert_grads_close(_grads(vl), grads_from(g, "tot_v_"), tol, "tot/v")
+    _zero(um, vm)
+    lv.backward()
+    assert_grads_close(_grads(ul), grads_from(g, "lv_u_"), tol, "lv/u")
+    assert_grads_close(_grads(vl), grads_from(g, "lv_v_"), tol, "lv/v")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("name,tech", [("ipw2d_fbc_11", "FBC"), ("ipw2d_fn_32", "FN")])
+def test_ipw2d(name, tech, dtype):
+    from pde_b200.schrodinger import ipw_2d as I
+    g = load_golden(name)
+    L, nx, ny = float(g["L"]), int(g["nx"]), int(g["ny"])
+    model = I.FCN([2, 16, 16, 16, 1], nx, ny, tech).double()
+    lin = _load(model.net, *net_from(g))
+    model = model.to("cuda", dtype)
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    y = torch.tensor(g["y"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = TOL[dtype]
+    lp = I.PINN_loss(model, x, y, nx, ny, L); lp.backward()
+    _close(lp, g["pinn_loss"], tol)
+    assert_grads_close(_grads(lin), grads_from(g, "pinn_"), tol, name + " pinn")
+    _zero(model)
+    ld = I.DRM_loss(model, x, y, L); ld.backward()
+    _close(ld, g["drm_loss"], tol)
+    assert_grads_close(_grads(lin), grads_from(g, "drm_"), 4 * tol, name + " drm")
+    _zero(model)
+    lo = I.orthogonal_loss(model, x, y, nx, ny, L)
+    _close(lo, g["orth_loss"], 4 * tol)
+    if "orth_gW0" in g:
+        lo.backward()
+        assert_grads_close(_grads(lin), grads_from(g, "orth_"), 4 * tol, name + " orth")
+    with pytest.raises(ValueError):
+        model.technique = "XX"
+        I.PINN_loss(model, x, y, nx, ny, L)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_qho2d_trainable_energy(dtype):
+    """QHO_2D_Energy.py: E_train.grad from the fused PINN launch."""
+    from pde_b200.schrodinger import qho_2d_energy as Q
+    g = load_golden("qho2d_energy_11")
+    L, nx, ny = float(g["L"]), int(g["nx"]), int(g["ny"])
+    model = Q.FCN([2, 16, 16, 16, 1], nx, ny, "FBC").double()
+    lin = _load(model.net, *net_from(g))
+    model = model.to("cuda", dtype)
+    E_train = torch.nn.Parameter(torch.tensor(float(g["E"]), dtype=dtype, device="cuda"))
+    x = torch.tensor(g["x"], dtype=dtype, device="cuda", requires_grad=True)
+    y = torch.tensor(g["y"], dtype=dtype, device="cuda", requires_grad=True)
+    tol = TOL[dtype]
+    lp = Q.PINN_loss(model, x, y, E_train, L); lp.backward()
+    _close(lp, g["pinn_loss"], tol)
+    assert_grads_close(_grads(lin), grads_from(g, "pinn_"), tol, "qho2d energy pinn")
+    _close(E_train.grad, g["pinn_gE"], tol)

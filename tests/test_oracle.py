@@ -215,3 +215,101 @@ def test_numpy_oracle_kh1d(name, kind):
     assert_grads_close(_combine(Gu, d), grads_from(g, "wan_u_"), 1e-8, "wan/u")
     assert_grads_close(_combine(Gv, d), grads_from(g, "wan_v_"), 1e-8, "wan/v")
     assert abs(d[0] * dE1 - float(g["wan_gE"])) <= 1e-8 * max(1, abs(float(g["wan_gE"])))
+
+
+# ---------------------------------------------------------------- second fixture set (make_golden.py more)
+def _qho1d_env(name, X_max, n):
+    from_nodes = {2: [-2 ** (-3 / 4), 2 ** (-3 / 4)], 3: [0.0, -2 ** (-3 / 4) * math.sqrt(3), 2 ** (-3 / 4) * math.sqrt(3)]}
+    nodes = [[float(np.float32(v)) for v in from_nodes[n]]] if "fn" in name else None   # float32 tensors in the reference
+    kind = O.ENV_NONE if "fnonly" in name else O.ENV_EXPWIN
+    return dict(kind=kind, lo=-X_max, hi=X_max, nodes=nodes)
+
+
+@pytest.mark.parametrize("name", ["qho1d_bc_n1", "qho1d_fn_n2", "qho1d_fnonly_n3"])
+def test_numpy_oracle_qho1d(name):
+    """QHO_1D_PINN_DRM.py:161-185 (ModuleList sine network, exp window and / or forced nodes)."""
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    X_max, n, X = float(g["X_max"]), int(g["n"]), g["x"]
+    env = _qho1d_env(name, X_max, n)
+    V = X ** 2          # 1/2 omega^2 x^2, omega = sqrt 2
+    loss, gWs, gbs, _ = O.eigen_pinn_loss(Ws, bs, X, O.SIN, env, alpha=-0.5, beta=V, E=(n + 0.5) * math.sqrt(2))
+    assert abs(loss - g["pinn_loss"]) <= 1e-10 * max(1, abs(g["pinn_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "pinn_"), 1e-9, name + " pinn")
+    loss, gWs, gbs, _ = O.rayleigh_loss(Ws, bs, X, O.SIN, env, a=0.5, beta=V)
+    assert abs(loss - g["drm_loss"]) <= 1e-10 * max(1, abs(g["drm_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "drm_"), 1e-9, name + " drm")
+    # value-only terms: (sqrt(sum u^2 dx) - 1)^2
+    J, _ = O.mlp_jets_forward(Ws, bs, X, O.SIN, 0)
+    U, _ = O.apply_envelope(J, X, 0, env["kind"], -X_max, X_max, env["nodes"])
+    dx = X[1, 0] - X[0, 0]
+    assert abs((math.sqrt((U ** 2).sum() * dx) - 1) ** 2 - g["norm_loss"]) <= 1e-10 * max(1, abs(g["norm_loss"]))
+
+
+def test_numpy_oracle_qho1d_wan():
+    """QHO_1D_WAN.py:115-140 with the trainable energy."""
+    g = load_golden("qho1d_wan_n1")
+    L, E, X = float(g["L"]), float(g["E"]), g["x"]
+    uW, ub = net_from(g, "u_"); vW, vb = net_from(g, "v_")
+    u_net = dict(Ws=uW, bs=ub, act=O.TANH, env=dict(kind=O.ENV_EXPWIN, lo=-L, hi=L))
+    v_net = dict(Ws=vW, bs=vb, act=O.TANH, env=dict(kind=O.ENV_NONE))
+    m, Gu, Gv, dE1 = O.wan_means(u_net, v_net, X, None, -L, L, a=0.5, beta=X ** 2, E=E)
+    m1, m2, m3, _ = m
+    lpde = m1 * m1 / (m2 + 1e-8)
+    lnorm = (2 * L * m3 - 1.0) ** 2
+    assert abs(lpde - g["loss_pde"]) <= 1e-9 * max(1, abs(g["loss_pde"]))
+    assert abs(lnorm - g["loss_norm"]) <= 1e-9 * max(1, abs(g["loss_norm"]))
+    dtot = [2 * m1 / (m2 + 1e-8), -m1 * m1 / (m2 + 1e-8) ** 2, 2 * (2 * L * m3 - 1.0) * 2 * L, 0.0]
+    assert_grads_close(_combine(Gu, dtot), grads_from(g, "tot_u_"), 1e-8, "tot/u")
+    assert_grads_close(_combine(Gv, dtot), grads_from(g, "tot_v_"), 1e-8, "tot/v")
+    assert abs(dtot[0] * dE1 - float(g["tot_gE"])) <= 1e-8 * max(1, abs(float(g["tot_gE"])))
+
+
+def test_numpy_oracle_ipw1d_wan_fn():
+    """IPW_1D_WAN_FN.py:91-118: forced nodes j L / n on u (n = 3) and none on v (n = 1)."""
+    g = load_golden("ipw1d_wanfn_n3")
+    L, n, X = float(g["L"]), int(g["n"]), g["x"]
+    uW, ub = net_from(g, "u_"); vW, vb = net_from(g, "v_")
+    u_net = dict(Ws=uW, bs=ub, act=O.TANH, env=dict(kind=O.ENV_POLY, lo=0.0, hi=L, nodes=[[j * L / n for j in range(1, n)]]))
+    v_net = dict(Ws=vW, bs=vb, act=O.TANH, env=dict(kind=O.ENV_POLY, lo=0.0, hi=L))
+    E = (n * math.pi) ** 2 / (2 * L * L)
+    m, Gu, Gv, _ = O.wan_means(u_net, v_net, X, None, 0.0, L, a=0.5, beta=None, E=E)
+    m1, m2, m3, _ = m
+    lpde = m1 * m1 / (m2 + 1e-8)
+    lnorm = (L * m3 - 1.0) ** 2
+    assert abs(lpde - g["loss_pde"]) <= 1e-9 * max(1, abs(g["loss_pde"]))
+    assert abs(lnorm - g["loss_norm"]) <= 1e-9 * max(1, abs(g["loss_norm"]))
+    dtot = [2 * m1 / (m2 + 1e-8), -m1 * m1 / (m2 + 1e-8) ** 2, 2 * (L * m3 - 1.0) * L, 0.0]
+    assert_grads_close(_combine(Gu, dtot), grads_from(g, "tot_u_"), 1e-8, "tot/u")
+    assert_grads_close(_combine(Gv, dtot), grads_from(g, "tot_v_"), 1e-8, "tot/v")
+
+
+@pytest.mark.parametrize("name", ["ipw2d_fbc_11", "ipw2d_fn_32"])
+def test_numpy_oracle_ipw2d(name):
+    """IPW_2D.py:195-228 inline PINN / DRM blocks."""
+    g = load_golden(name)
+    Ws, bs = net_from(g)
+    L, nx, ny = float(g["L"]), int(g["nx"]), int(g["ny"])
+    X = np.stack([g["x"].reshape(-1), g["y"].reshape(-1)], axis=1)
+    nodes = [[k * L / nx for k in range(1, nx)], [k * L / ny for k in range(1, ny)]] if "fn" in name else None
+    env = dict(kind=O.ENV_POLY, lo=0.0, hi=L, nodes=nodes)
+    k2 = (nx * math.pi / L) ** 2 + (ny * math.pi / L) ** 2
+    loss, gWs, gbs, _ = O.eigen_pinn_loss(Ws, bs, X, O.SIN, env, alpha=1.0, beta=k2, E=0.0)
+    assert abs(loss - g["pinn_loss"]) <= 1e-10 * max(1, abs(g["pinn_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "pinn_"), 1e-9, name + " pinn")
+    loss, gWs, gbs, _ = O.rayleigh_loss(Ws, bs, X, O.SIN, env, a=1.0, beta=None, eps_in=1e-8)
+    assert abs(loss - g["drm_loss"]) <= 1e-10 * max(1, abs(g["drm_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "drm_"), 1e-9, name + " drm")
+
+
+def test_numpy_oracle_qho2d_energy():
+    """QHO_2D_Energy.py:382-383: dLoss/dE of the PINN residual with a trainable energy."""
+    g = load_golden("qho2d_energy_11")
+    Ws, bs = net_from(g)
+    L, E = float(g["L"]), float(g["E"])
+    X = np.stack([g["x"].reshape(-1), g["y"].reshape(-1)], axis=1)
+    V = X[:, 0:1] ** 2 + X[:, 1:2] ** 2
+    loss, gWs, gbs, dE = O.eigen_pinn_loss(Ws, bs, X, O.SIN, dict(kind=O.ENV_EXPWIN, lo=-L, hi=L), alpha=-0.5, beta=V, E=E)
+    assert abs(loss - g["pinn_loss"]) <= 1e-10 * max(1, abs(g["pinn_loss"]))
+    assert_grads_close((gWs, gbs), grads_from(g, "pinn_"), 1e-9, "qho2d energy pinn")
+    assert abs(dE - float(g["pinn_gE"])) <= 1e-9 * max(1, abs(float(g["pinn_gE"])))
