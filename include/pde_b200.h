@@ -162,6 +162,44 @@ int pde_wan_pointwise(const pde_wan* wan, const void* X, int64_t n_points, const
                       const void* Jv, const void* seed, double inv_n, void* sums, void* Jbar_u,
                       void* Jbar_v, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the device-side pieces of an epoch around the loss step (all single launches, graph capturable) ---- */
+
+/* Collocation-point sampling with the manufactured solution / right-hand side in the same pass.
+ * Replaces: sample_interior (Poisson_ND.py:187-190: X = rand(N, d) * L), exact_u_prod_sin and
+ * rhs_f_for_u_sin (Poisson_ND.py:49-58), and the test-point draw of the L2 evaluation (:281-285).
+ *   X (n, dim) out: lo + (hi-lo) * U[0,1), Philox4x32-10 keyed by `seed`, counter = (point index, `offset`
+ *                   + *offset_add when that optional device int64 is given, e.g. the Adam step counter, so
+ *                   that a replayed CUDA graph draws fresh points every epoch);
+ *                   statistically equivalent to torch.rand, not bit-identical.
+ *   X_in: when non-NULL the points are read from X_in instead of sampled (X may be NULL).
+ *   k (host, dim) and period: u_exact = prod_i sin(k_i pi x_i / period), f = sum_i (k_i pi / period)^2 u_exact;
+ *   u_exact, f: device (n) out, each optional. */
+int pde_sample_points_rhs(int32_t dtype, int32_t dim, int64_t n_points, double lo, double hi, uint64_t seed,
+                          uint64_t offset, const void* offset_add, const double* k, double period,
+                          const void* X_in, void* X, void* u_exact, void* f, void* stream);
+
+/* Fused Adam over the flat gradient vector that pde_residual_loss_grad writes (parameters() order, a
+ * trailing trainable energy scalar included when it is listed as the last tensor).
+ * Replaces: torch.optim.Adam(model.parameters(), lr).step() (Poisson_ND.py:177,240; KH_1D.py:330-336).
+ *   m += (1-beta1)(g-m);  v = beta2 v + (1-beta2) g^2;  p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)
+ *   with g = grad_scale * grad_flat[i] (+ weight_decay * p), t = *step + 1; *step is incremented (device int64). */
+typedef struct pde_adam {
+  int32_t dtype;
+  int32_t n_tensors;                      /* 1 .. 2*PDE_MAX_LINEAR+1 */
+  double lr, beta1, beta2, eps, weight_decay, grad_scale;
+  void* param[2 * PDE_MAX_LINEAR + 1];    /* device: the nn.Parameter storages, updated in place */
+  int64_t numel[2 * PDE_MAX_LINEAR + 1];
+} pde_adam;
+
+int pde_adam_step(const pde_adam* cfg, const void* grad_flat, void* exp_avg, void* exp_avg_sq, void* step,
+                  void* stream);
+
+/* Device-side best-model tracking: if *metric < *best_metric, copy every parameter tensor into best_flat
+ * and update *best_metric (and *best_step = *step when both are given).  No host read-back.
+ * Replaces: the per-epoch `.item()` + state_dict copy to the CPU (Poisson_ND.py:288-300). */
+int pde_keep_best(const pde_adam* cfg, const void* metric, void* best_metric, void* best_flat, const void* step,
+                  void* best_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

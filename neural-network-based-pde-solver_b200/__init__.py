@@ -14,6 +14,7 @@ from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, all_reduce_gr
                   wan_means)
 from . import poisson
 from . import schrodinger
+from . import train
 
 __all__ = ["PdeError", "load_library", "EnvelopeSpec", "ProgramSpec", "WanSpec", "NO_ENVELOPE", "mlp_jets",
-           "residual_means", "wan_means", "all_reduce_grads", "poisson", "schrodinger"]
+           "residual_means", "wan_means", "all_reduce_grads", "poisson", "schrodinger", "train"]

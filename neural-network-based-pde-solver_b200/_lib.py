@@ -17,7 +17,8 @@ PROG_PINN, PROG_DRM, PROG_RAYLEIGH, PROG_MSE = 1, 2, 3, 4
 EXPORTS = [
     "pde_abi_version", "pde_strerror", "pde_param_count", "pde_jet_channels", "pde_program_quantities",
     "pde_program_order", "pde_workspace_bytes", "pde_jets_forward", "pde_jets_backward",
-    "pde_residual_loss_grad", "pde_wan_pointwise", "pde_query_path",
+    "pde_residual_loss_grad", "pde_wan_pointwise", "pde_query_path", "pde_sample_points_rhs", "pde_adam_step",
+    "pde_keep_best",
 ]
 
 
@@ -41,6 +42,12 @@ class Wan(C.Structure):
                 ("energy_const", C.c_double), ("w_lo", C.c_double), ("w_hi", C.c_double), ("eps_den", C.c_double),
                 ("f", C.c_void_p), ("beta", C.c_void_p), ("energy", C.c_void_p),
                 ("env_u", Envelope), ("env_v", Envelope)]
+
+
+class Adam(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("n_tensors", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double), ("grad_scale", C.c_double),
+                ("param", C.c_void_p * (2 * MAX_LINEAR + 1)), ("numel", C.c_int64 * (2 * MAX_LINEAR + 1))]
 
 
 class PdeError(RuntimeError):
@@ -79,6 +86,10 @@ def load():
                                            vp, vp, vp, vp, sz, vp]
     lib.pde_query_path.argtypes = [C.POINTER(Net), C.POINTER(Program), i64]
     lib.pde_wan_pointwise.argtypes = [C.POINTER(Wan), vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, sz, vp]
+    lib.pde_sample_points_rhs.argtypes = [i32, i32, i64, dbl, dbl, C.c_uint64, C.c_uint64, vp, C.POINTER(dbl), dbl, vp, vp,
+                                          vp, vp, vp]
+    lib.pde_adam_step.argtypes = [C.POINTER(Adam), vp, vp, vp, vp, vp]
+    lib.pde_keep_best.argtypes = [C.POINTER(Adam), vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("pde_strerror",):
             getattr(lib, name).restype = C.c_int
