@@ -10,11 +10,11 @@ gradient, behind the reference's own loss-function signatures.
 """
 from . import _lib
 from ._lib import PdeError, load as load_library
-from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, all_reduce_grads, mlp_jets, residual_means,
-                  wan_means)
+from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, all_reduce_grads, frozen_jets, mlp_jets,
+                  residual_means, wan_means)
 from . import poisson
 from . import schrodinger
 from . import train
 
 __all__ = ["PdeError", "load_library", "EnvelopeSpec", "ProgramSpec", "WanSpec", "NO_ENVELOPE", "mlp_jets",
-           "residual_means", "wan_means", "all_reduce_grads", "poisson", "schrodinger", "train"]
+           "residual_means", "wan_means", "frozen_jets", "all_reduce_grads", "poisson", "schrodinger", "train"]

@@ -480,13 +480,17 @@ class _WanPoint(torch.autograd.Function):
 
 
 def wan_means(u_model, v_model, X, spec: WanSpec, env_u=NO_ENVELOPE, env_v=NO_ENVELOPE, f=None, beta=None, energy=None,
-              group=None, n_global=None):
+              group=None, n_global=None, u_jets=None, v_jets=None):
     """means (q0..q3) of the WAN weak-form quantities for the u / v networks (pde_wan_pointwise).
 
     The jets of both networks come from the fused network kernels; parameters with
     ``requires_grad=False`` (the reference toggles them, IPW_1D_WAN.py:186-200) get no gradient.
     With ``group`` the per-rank parameter gradients are averaged exactly because the means are
     all-reduced before ``F`` is applied and the cotangents carry 1/N_global.
+
+    ``u_jets`` / ``v_jets``: order-1 jets of a *frozen* network on the same points (``frozen_jets``),
+    reused instead of re-evaluating that network — the critic steps of the minimax loop run on fixed
+    points with the other network's parameters switched off (IPW_1D_WAN.py:186-194, KH_1D.py:343-352).
     """
     X = _points(X)
     n = X.shape[0]
@@ -505,10 +509,24 @@ def wan_means(u_model, v_model, X, spec: WanSpec, env_u=NO_ENVELOPE, env_v=NO_EN
     if beta is not None and not torch.is_tensor(beta):
         spec = WanSpec(spec.alpha, float(beta), spec.energy_const, spec.w_lo, spec.w_hi, spec.eps_den)
         beta = None
-    Ju = mlp_jets(u_model, X, 1)
-    Jv = mlp_jets(v_model, X, 1)
+    Ju = mlp_jets(u_model, X, 1) if u_jets is None else _check_jets(u_jets, X)
+    Jv = mlp_jets(v_model, X, 1) if v_jets is None else _check_jets(v_jets, X)
     means = _WanPoint.apply(spec, env_u, env_v, group, n_global, X, coef(f), coef(beta), e, Ju, Jv)
     return means
+
+
+def _check_jets(J, X):
+    if J.shape != (X.shape[0], 1 + X.shape[1]) or J.dtype != X.dtype or J.device != X.device:
+        raise ValueError("frozen jets must be the (N, 1+d) order-1 jets of the same points")
+    return J.detach()
+
+
+def frozen_jets(model, X, order: int = 1):
+    """Jets of a network whose parameters are not being trained in this phase: one forward launch,
+    no autograd node.  Pass the result as ``u_jets`` / ``v_jets`` to the WAN losses for as long as
+    neither the points nor that network change."""
+    with torch.no_grad():
+        return mlp_jets(model, X, order).detach()
 
 
 def all_reduce_grads(params, group=None):

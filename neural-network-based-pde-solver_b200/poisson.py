@@ -101,11 +101,12 @@ def drm_energy_loss(model, X_in, f_in, L, *, group=None, n_global=None):
     return m[0]
 
 
-def wan_losses(u_model, v_model, X, f_vals, L, eps=1e-8, v_reg_weight=0.0, *, group=None, n_global=None):
+def wan_losses(u_model, v_model, X, f_vals, L, eps=1e-8, v_reg_weight=0.0, *, group=None, n_global=None,
+               u_jets=None, v_jets=None):
     """(loss_pde_u, loss_v, weak_residual, phi_norm)   (Poisson_ND.py:105-128)."""
     assert X.requires_grad, "X must require_grad=True"
     m = wan_means(u_model, v_model, X, WanSpec(alpha=1.0, w_lo=0.0, w_hi=float(L)), env_u=_envelope(u_model, L),
-                  env_v=NO_ENVELOPE, f=f_vals, group=group, n_global=n_global)
+                  env_v=NO_ENVELOPE, f=f_vals, group=group, n_global=n_global, u_jets=u_jets, v_jets=v_jets)
     weak, phi_norm, v_reg = m[0], m[1], m[3]
     loss_pde_u = weak ** 2 / (phi_norm + eps)
     loss_v = -torch.log(loss_pde_u + eps) + v_reg_weight * v_reg

@@ -34,10 +34,10 @@ def _envelope(model):
     return poly_envelope(L, [[j * L / n for j in range(1, n)]])
 
 
-def WAN_loss(u_model, v_model, x, n, L, weight_pde=1.0, weight_norm=1.0):
+def WAN_loss(u_model, v_model, x, n, L, weight_pde=1.0, weight_norm=1.0, *, u_jets=None, v_jets=None):
     """(total_loss, loss_v, loss_pde, loss_norm)   (IPW_1D_WAN_FN.py:91-118)."""
     m = wan_means(u_model, v_model, x, WanSpec(alpha=0.5, energy_const=Exact_energy(n, L), w_lo=0.0, w_hi=float(L)),
-                  env_u=_envelope(u_model), env_v=_envelope(v_model))
+                  env_u=_envelope(u_model), env_v=_envelope(v_model), u_jets=u_jets, v_jets=v_jets)
     loss_pde = m[0] ** 2 / (m[1] + 1e-8)
     loss_norm = (L * m[2] - 1.0) ** 2
     total_loss = weight_pde * loss_pde + weight_norm * loss_norm

@@ -98,11 +98,12 @@ def drm_loss(model, x, alpha, V0, L, use_avg=True, n_theta=500):
     return (2 * L) * m[0] / ((2 * L) * m[1] + 1e-12)
 
 
-def wan_loss(model, v_model, x, alpha, V0, L, use_avg=True, n_theta=500):
+def wan_loss(model, v_model, x, alpha, V0, L, use_avg=True, n_theta=500, *, u_jets=None, v_jets=None):
     """(pde_loss, norm_u)   (KH_1D.py:244-269): (I_full / ||phi||^2)^2 and (int u^2 - 1)^2."""
     Vx = _potential(x, alpha, V0, use_avg, n_theta)
     m = wan_means(model, v_model, x, WanSpec(alpha=0.5, w_lo=-float(L), w_hi=float(L), eps_den=1e-10),
-                  env_u=_envelope(model, L), env_v=_envelope(v_model, L), beta=Vx, energy=model.energy)
+                  env_u=_envelope(model, L), env_v=_envelope(v_model, L), beta=Vx, energy=model.energy,
+                  u_jets=u_jets, v_jets=v_jets)
     I_full = (2 * L) * m[0]
     norm_phi = (2 * L) * m[1] + 1e-12
     return (I_full / norm_phi) ** 2, ((2 * L) * m[2] - 1.0) ** 2

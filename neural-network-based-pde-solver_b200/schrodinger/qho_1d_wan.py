@@ -32,13 +32,13 @@ def _envelope(model):
     return window_envelope(float(model.L)) if getattr(model, "enforce_bc", False) else NO_ENVELOPE
 
 
-def WAN_loss(u_model, v_model, x, n, L, weight_pde=1.0, weight_norm=1.0):
+def WAN_loss(u_model, v_model, x, n, L, weight_pde=1.0, weight_norm=1.0, *, u_jets=None, v_jets=None):
     """(total_loss, loss_v, loss_pde, loss_norm)   (QHO_1D_WAN.py:115-140): weak residual of
     -1/2 u'' + V u = E u against phi = w v with E = ``u_model.energies`` (trainable),
     plus (2 L mean(u^2) - 1)^2."""
     V = Potential(x.detach())
     m = wan_means(u_model, v_model, x, WanSpec(alpha=0.5, w_lo=-float(L), w_hi=float(L)),
-                  env_u=_envelope(u_model), env_v=_envelope(v_model), beta=V, energy=u_model.energies)
+                  env_u=_envelope(u_model), env_v=_envelope(v_model), beta=V, energy=u_model.energies, u_jets=u_jets, v_jets=v_jets)
     loss_pde = m[0] ** 2 / (m[1] + 1e-8)
     loss_norm = (2 * L * m[2] - 1.0) ** 2
     total_loss = weight_pde * loss_pde + weight_norm * loss_norm

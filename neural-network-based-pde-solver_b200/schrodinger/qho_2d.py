@@ -85,12 +85,12 @@ def DRM_loss(model, x, y, L=6.0):
     return m[0] / (m[1] + 1e-8)
 
 
-def WAN_loss(u_model, v_model, x, y, nx, ny, L, weight_pde=1.0, weight_norm=1.0):
+def WAN_loss(u_model, v_model, x, y, nx, ny, L, weight_pde=1.0, weight_norm=1.0, *, u_jets=None, v_jets=None):
     """(total_loss, loss_v, loss_pde, loss_norm)   (QHO_2D.py:204-225)."""
     X, V = _points(x, y)
     m = wan_means(u_model, v_model, X, WanSpec(alpha=0.5, energy_const=Exact_energy(nx, ny, L), w_lo=-float(L), w_hi=float(L),
                                                eps_den=1e-10),
-                  env_u=_envelope(u_model, L), env_v=_envelope(v_model, L), beta=V)
+                  env_u=_envelope(u_model, L), env_v=_envelope(v_model, L), beta=V, u_jets=u_jets, v_jets=v_jets)
     loss_pde = m[0] ** 2 / (m[1] + 1e-8)
     loss_norm = (4 * L * L * m[2] - 1.0) ** 2
     total_loss = weight_pde * loss_pde + weight_norm * loss_norm

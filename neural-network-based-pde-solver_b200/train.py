@@ -253,3 +253,56 @@ class FusedTrainer:
             for p in tgt:
                 k = p.numel()
                 p.copy_(self.best_flat[o:o + k].view_as(p)); o += k
+
+
+class GraphedEpoch:
+    """Capture a reference-style epoch — ``zero_grad -> losses -> backward -> optimizer.step`` written
+    against the drop-in loss functions — into one CUDA graph and replay it.
+
+    The drop-in operators enqueue everything on the current stream and never synchronise, so the host
+    side of an epoch (Python, autograd bookkeeping, ~20 small launches per loss) disappears on replay;
+    this is what makes the latency-bound configurations (1 000 – 40 000 points: IPW / QHO / KH grids,
+    BASELINE.json configs 1, 4, 5) run at kernel speed.  Requirements on ``fn``: static input tensors,
+    no ``.item()`` / host read-back inside, optimisers built with ``capturable=True``, gradients
+    allocated before capture (``warmup`` eager epochs on a side stream take care of that).
+
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+        def epoch():
+            opt.zero_grad(set_to_none=False)
+            loss = I.PINN_loss(model, x, n, L); loss.backward(); opt.step()
+            return loss
+        ep = pb.train.GraphedEpoch(epoch); ep(); ...; print(float(ep.out))
+    """
+
+    def __init__(self, fn, warmup=3, device=None):
+        self.fn = fn
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.graph = None
+        self.out = None
+        self.warmup = int(warmup)
+        self.replays = 0
+
+    def _capture(self):
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self.out = self.fn()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.out = self.fn()
+        self.graph = g
+
+    def __call__(self):
+        """Run one epoch; returns ``fn``'s output tensors (static storage, overwritten by every replay).
+        The first call runs ``warmup`` eager epochs and captures; it does not replay, so that the number
+        of optimiser steps taken equals ``warmup`` after it (then +1 per call)."""
+        with torch.cuda.device(self.dev):
+            if self.graph is None:
+                self._capture()
+            else:
+                self.graph.replay()
+                self.replays += 1
+        return self.out

@@ -147,3 +147,76 @@ def test_trainer_resamples_every_epoch():
         Xe, _, fe = pb.train.sample_points_rhs(8192, 2, 2.0, [1, 2], seed=9, offset=e)
         assert torch.equal(seen[e], Xe)
     assert torch.isfinite(tr.hist_loss).all()
+
+
+def test_wan_frozen_jets_give_identical_losses_and_grads():
+    """§8f-2: the critic steps reuse the frozen u-network's jets on fixed points (IPW_1D_WAN.py:186-194)."""
+    from pde_b200.schrodinger import ipw_1d_wan as W
+    torch.manual_seed(2)
+    L, n = 2.0, 2
+    um = W.FCN([1, 50, 50, 50, 1], L=L, enforce_bc=True).cuda()
+    vm = W.FCN([1, 20, 20, 20, 1], L=L).cuda()
+    x = torch.linspace(0, L, 1000, device="cuda").view(-1, 1).requires_grad_(True)
+    for p in um.parameters():
+        p.requires_grad_(False)
+    _, lv_a, lp_a, _ = W.WAN_loss(um, vm, x, n, L)
+    lv_a.backward()
+    ga = [p.grad.clone() for p in vm.parameters()]
+    for p in vm.parameters():
+        p.grad = None
+    Ju = pb.frozen_jets(um, x)
+    _, lv_b, lp_b, _ = W.WAN_loss(um, vm, x, n, L, u_jets=Ju)
+    lv_b.backward()
+    assert torch.equal(lv_a, lv_b) and torch.equal(lp_a, lp_b)
+    for a, p in zip(ga, vm.parameters()):
+        assert torch.equal(a, p.grad)
+    assert all(p.grad is None for p in um.parameters())
+    with pytest.raises(ValueError):
+        W.WAN_loss(um, vm, x, n, L, u_jets=Ju[:10])
+
+
+def test_graphed_wan_epoch_matches_eager():
+    """One epoch of the IPW 1-D WAN loop (5 critic steps + 1 solution step, IPW_1D_WAN.py:186-208) captured as a
+    CUDA graph equals the same epoch run eagerly."""
+    from pde_b200.schrodinger import ipw_1d_wan as W
+    L, n = 2.0, 2
+    x = torch.linspace(0, L, 1000, device="cuda").view(-1, 1)
+
+    def build():
+        torch.manual_seed(4)
+        um = W.FCN([1, 50, 50, 50, 1], L=L, enforce_bc=True).cuda()
+        vm = W.FCN([1, 20, 20, 20, 1], L=L).cuda()
+        ou = torch.optim.Adam(um.parameters(), lr=1e-3, capturable=True)
+        ov = torch.optim.Adam(vm.parameters(), lr=1e-3, capturable=True)
+
+        def epoch():
+            Ju = pb.frozen_jets(um, x)
+            for _ in range(5):
+                ov.zero_grad(set_to_none=False)
+                _, lv, _, _ = W.WAN_loss(um, vm, x, n, L, u_jets=Ju)
+                gv = torch.autograd.grad(lv, list(vm.parameters()))
+                for p, g in zip(vm.parameters(), gv):
+                    p.grad = g if p.grad is None else p.grad.copy_(g)
+                ov.step()
+            ou.zero_grad(set_to_none=False)
+            total, _, lp, ln = W.WAN_loss(um, vm, x, n, L)
+            gu = torch.autograd.grad(total, list(um.parameters()))
+            for p, g in zip(um.parameters(), gu):
+                p.grad = g if p.grad is None else p.grad.copy_(g)
+            ou.step()
+            return total.detach()
+        return um, vm, epoch
+
+    um1, vm1, ep1 = build()
+    for _ in range(6):
+        t1 = ep1()
+    um2, vm2, ep2 = build()
+    g = pb.train.GraphedEpoch(ep2, warmup=3)
+    g()                      # 3 eager epochs + capture
+    for _ in range(3):
+        t2 = g()             # 3 replays
+    torch.cuda.synchronize()
+    assert g.replays == 3
+    for a, b in zip(list(um1.parameters()) + list(vm1.parameters()), list(um2.parameters()) + list(vm2.parameters())):
+        assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
+    assert abs(float(t1) - float(t2)) <= 1e-5 * max(1e-3, abs(float(t1)))
