@@ -159,10 +159,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
+    exchange = "none (one rank)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+        # exchange step: one kernel over NVLink peer memory (pde_allreduce_oneshot); PDE_B200_EXCHANGE=nccl keeps NCCL
+        if os.environ.get("PDE_B200_EXCHANGE", "nvlink") == "nvlink":
+            try:
+                ops.use_nvlink_exchange(None, 1 << 15, torch.float32)
+                exchange = "one-kernel NVLink peer-memory all-reduce (pde_allreduce_oneshot)"
+            except Exception as exc:             # e.g. CUDA IPC unavailable in this container
+                exchange = f"NCCL all-reduce (NVLink exchange unavailable: {type(exc).__name__})"
+        else:
+            exchange = "NCCL all-reduce"
     N = args.points
     n_global = N * world
 
@@ -277,7 +287,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "points_per_gpu": N, "global_points": n_global,
-                       "parallelism": f"dp{world} over points, one NCCL all-reduce of [grad|sum] per step",
+                       "parallelism": f"dp{world} over points, one all-reduce of [grad|dE|sum] (51 KB) per step", "exchange": exchange,
                        "l2": "4 rotating point sets (256 MiB) > 126 MB L2", "kernel_path": pb.ops.last_kernel_path()},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -34,6 +34,7 @@ extern "C" {
 #define PDE_MAX_NODES 8    /* forced-node roots per dimension */
 #define PDE_MAX_Q 4        /* per-point quantities a program may average */
 #define PDE_MAX_WIDTH 256  /* hidden width */
+#define PDE_MAX_PEERS 8    /* GPUs of one NVSwitch box */
 
 typedef enum {
   PDE_OK = 0,
@@ -199,6 +200,32 @@ int pde_adam_step(const pde_adam* cfg, const void* grad_flat, void* exp_avg, voi
  * Replaces: the per-epoch `.item()` + state_dict copy to the CPU (Poisson_ND.py:288-300). */
 int pde_keep_best(const pde_adam* cfg, const void* metric, void* best_metric, void* best_flat, const void* step,
                   void* best_step, void* stream);
+
+/* ---- exchange step of the data-parallel loss step over NVLink peer memory (one kernel, no NCCL call) ---- */
+
+/* Peer-visible buffers: plain device allocations shared through CUDA IPC handles (64 bytes, exchanged by
+ * the host side once at set-up).  pde_peer_bytes gives the size for a given slot capacity:
+ * [signal pad | slot parity 0 | slot parity 1]. */
+int pde_peer_bytes(int32_t dtype, int64_t slot_elems, size_t* bytes);
+int pde_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);   /* cudaMalloc + zero + cudaIpcGetMemHandle */
+int pde_peer_open(const unsigned char* handle64, void** ptr);            /* cudaIpcOpenMemHandle (another process' buffer) */
+int pde_peer_close(void* ptr);
+int pde_peer_free(void* ptr);
+
+typedef struct pde_peers {
+  int32_t rank, world;             /* world <= PDE_MAX_PEERS */
+  void* base[PDE_MAX_PEERS];       /* base[r]: rank r's buffer as mapped in THIS process (own allocation at base[rank]) */
+} pde_peers;
+
+/* In-place sum of `buf` (n values) over the ranks of one box: copy-in to the rank's slot, system-scope
+ * signal / wait on every peer's pad, then every rank adds all slots in rank order (bit-identical result on
+ * every rank, independent of arrival order).  One thread block, one launch; `seq` (device uint32, zero at
+ * start) counts the calls so the kernel can be replayed from a CUDA graph.  A peer that does not arrive
+ * within ~2 s poisons the result with NaN instead of hanging the GPU.
+ * Replaces: the gradient exchange a data-parallel run of train_poisson_nd needs after loss.backward()
+ * (Poisson_ND.py:240; the reference itself is single-device), SURVEY.md §8e. */
+int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int64_t n, int64_t slot_elems,
+                          void* seq, void* stream);
 
 #ifdef __cplusplus
 }

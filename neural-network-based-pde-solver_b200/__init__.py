@@ -15,6 +15,7 @@ from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, all_reduce_gr
 from . import poisson
 from . import schrodinger
 from . import train
+from . import comm
 
 __all__ = ["PdeError", "load_library", "EnvelopeSpec", "ProgramSpec", "WanSpec", "NO_ENVELOPE", "mlp_jets",
-           "residual_means", "wan_means", "frozen_jets", "all_reduce_grads", "poisson", "schrodinger", "train"]
+           "residual_means", "wan_means", "frozen_jets", "all_reduce_grads", "poisson", "schrodinger", "train", "comm"]

@@ -18,8 +18,10 @@ EXPORTS = [
     "pde_abi_version", "pde_strerror", "pde_param_count", "pde_jet_channels", "pde_program_quantities",
     "pde_program_order", "pde_workspace_bytes", "pde_jets_forward", "pde_jets_backward",
     "pde_residual_loss_grad", "pde_wan_pointwise", "pde_query_path", "pde_sample_points_rhs", "pde_adam_step",
-    "pde_keep_best",
+    "pde_keep_best", "pde_peer_bytes", "pde_peer_alloc", "pde_peer_open", "pde_peer_close", "pde_peer_free",
+    "pde_allreduce_oneshot",
 ]
+MAX_PEERS = 8
 
 
 class Net(C.Structure):
@@ -48,6 +50,10 @@ class Adam(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("n_tensors", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double), ("grad_scale", C.c_double),
                 ("param", C.c_void_p * (2 * MAX_LINEAR + 1)), ("numel", C.c_int64 * (2 * MAX_LINEAR + 1))]
+
+
+class Peers(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("base", C.c_void_p * MAX_PEERS)]
 
 
 class PdeError(RuntimeError):
@@ -90,6 +96,12 @@ def load():
                                           vp, vp, vp]
     lib.pde_adam_step.argtypes = [C.POINTER(Adam), vp, vp, vp, vp, vp]
     lib.pde_keep_best.argtypes = [C.POINTER(Adam), vp, vp, vp, vp, vp, vp]
+    lib.pde_peer_bytes.argtypes = [i32, i64, C.POINTER(sz)]
+    lib.pde_peer_alloc.argtypes = [sz, C.POINTER(vp), C.c_char_p]
+    lib.pde_peer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.pde_peer_close.argtypes = [vp]
+    lib.pde_peer_free.argtypes = [vp]
+    lib.pde_allreduce_oneshot.argtypes = [C.POINTER(Peers), i32, vp, i64, i64, vp, vp]
     for name in EXPORTS:
         if name not in ("pde_strerror",):
             getattr(lib, name).restype = C.c_int

@@ -224,6 +224,21 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
   asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
+// stash store policy (development switch): 0 = st.global.cg (L2 only), 1 = default st.global (write-through L1), 2 = st.global.cs
+#ifndef PDE_TC_STASH_ST
+#define PDE_TC_STASH_ST 0
+#endif
+__device__ __forceinline__ void stash_store(float4* p, float4 v) {
+#if PDE_TC_STASH_ST == 1
+  *p = v;
+#elif PDE_TC_STASH_ST == 2
+  __stcs(p, v);
+#elif PDE_TC_STASH_ST == 3   // timing experiment only: no store (wrong results)
+  (void)p; (void)v;
+#else
+  __stcg(p, v);
+#endif
+}
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // UMMA descriptors as "constant high word + 14-bit start address (16-byte units) in the low word":
@@ -716,11 +731,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
           }
           if (do_bwd) {
-            __stcg(stash_at(l, j, 0), make_float4(sv0[0], sv0[1], sv0[2], sv0[3]));
-            __stcg(stash_at(l, j, 1), make_float4(sv1[0], sv1[1], sv1[2], sv1[3]));
+            stash_store(stash_at(l, j, 0), make_float4(sv0[0], sv0[1], sv0[2], sv0[3]));
+            stash_store(stash_at(l, j, 1), make_float4(sv1[0], sv1[1], sv1[2], sv1[3]));
             if constexpr (!L0) {
 #pragma unroll
-              for (int c = 1; c < C; ++c) __stcg(stash_at(l, j, 1 + c), make_float4(z[c][0], z[c][1], z[c][2], z[c][3]));
+              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), make_float4(z[c][0], z[c][1], z[c][2], z[c][3]));
             }
           }
           if (!L0 && j < 3) {

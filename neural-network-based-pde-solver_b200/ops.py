@@ -196,9 +196,27 @@ def _points(X):
     return X.detach().contiguous()
 
 
+_EXCHANGE = {}   # process group -> comm.NvlinkAllReduce registered by use_nvlink_exchange
+
+
+def use_nvlink_exchange(group=None, max_elems=1 << 17, dtype=torch.float32):
+    """Route the exchange step of ``residual_means`` / ``wan_means`` for ``group`` through the one-kernel
+    NVLink all-reduce (pde_allreduce_oneshot) instead of NCCL.  Returns the communicator."""
+    from .comm import NvlinkAllReduce
+    import torch.distributed as dist
+    key = (group if group is not None else dist.group.WORLD, dtype)
+    if key not in _EXCHANGE:
+        _EXCHANGE[key] = NvlinkAllReduce(group, max_elems, dtype)
+    return _EXCHANGE[key]
+
+
 def _all_reduce(t, group):
     import torch.distributed as dist
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    ar = _EXCHANGE.get((group if group is not None else dist.group.WORLD, t.dtype)) if _EXCHANGE else None
+    if ar is not None and t.is_cuda and t.is_contiguous() and t.numel() <= ar.slot:
+        ar.all_reduce_(t)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
 def combine_forward(buf, nparam, n_tot, group, fused):

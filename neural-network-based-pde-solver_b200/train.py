@@ -105,11 +105,14 @@ class FusedTrainer:
     n_test     > 0: L2 evaluation on freshly drawn test points after each step and device-side
                best-parameter tracking (:281-300)
     history    number of epochs whose loss (and L2) are kept in device arrays (0: none)
+    group      data parallelism over points: every rank runs the same epoch on its own points and the
+               [grad | dE | sums] vector is summed over the ranks before Adam (exchange='nvlink': one
+               kernel over peer memory; 'nccl': torch.distributed.all_reduce)
     """
 
     def __init__(self, model, L_box=2.0, ks=None, method='PINN', n_interior=20000, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  weight_pde=1.0, X=None, f=None, resample=False, seed=0, n_test=0, history=0, graph=True, group=None,
-                 envelope: Optional[EnvelopeSpec] = None):
+                 envelope: Optional[EnvelopeSpec] = None, exchange='nvlink'):
         from .poisson import _envelope
         self.lib = L.load()
         self.model, self.L, self.method, self.group = model, float(L_box), method, group
@@ -138,9 +141,15 @@ class FusedTrainer:
         self.opt = FusedAdam([p.data for p in self.params], lr=lr, betas=betas, eps=eps)
         self.weight_pde = float(weight_pde)
         self.world = 1
+        self._ar = None
         if group is not None:
             import torch.distributed as dist
             self.world = dist.get_world_size(group)
+            if exchange == 'nvlink':     # one-kernel all-reduce over peer memory (pde_allreduce_oneshot)
+                from .comm import NvlinkAllReduce
+                self._ar = NvlinkAllReduce(group, self.nparam + 2, self.dtype, self.dev)
+            elif exchange != 'nccl':
+                raise ValueError("exchange must be 'nvlink' or 'nccl'")
         # [grad (nparam) | dE (1) | sums (K)] — the layout pde_residual_loss_grad writes and Adam reads
         self.buf = torch.zeros(self.nparam + 2, dtype=self.dtype, device=self.dev)
         self.n_test = int(n_test)
@@ -182,7 +191,9 @@ class FusedTrainer:
                                            self.buf.data_ptr() + (self.nparam + 1) * es, self.buf.data_ptr(),
                                            self.buf.data_ptr() + self.nparam * es, self._ws.data_ptr(), self._ws.numel(), st),
                 "pde_residual_loss_grad")
-        if self.group is not None:
+        if self._ar is not None:
+            self._ar.all_reduce_(self.buf)
+        elif self.group is not None:
             import torch.distributed as dist
             dist.all_reduce(self.buf, group=self.group)
         if self.hist_loss.numel():
