@@ -205,7 +205,7 @@ int pde_keep_best(const pde_adam* cfg, const void* metric, void* best_metric, vo
 
 /* Peer-visible buffers: plain device allocations shared through CUDA IPC handles (64 bytes, exchanged by
  * the host side once at set-up).  pde_peer_bytes gives the size for a given slot capacity:
- * [signal pad | slot parity 0 | slot parity 1]. */
+ * [signal pad | slot parity 0 | slot parity 1]; slot_elems must be a multiple of 4. */
 int pde_peer_bytes(int32_t dtype, int64_t slot_elems, size_t* bytes);
 int pde_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);   /* cudaMalloc + zero + cudaIpcGetMemHandle */
 int pde_peer_open(const unsigned char* handle64, void** ptr);            /* cudaIpcOpenMemHandle (another process' buffer) */
@@ -219,7 +219,7 @@ typedef struct pde_peers {
 
 /* In-place sum of `buf` (n values) over the ranks of one box: copy-in to the rank's slot, system-scope
  * signal / wait on every peer's pad, then every rank adds all slots in rank order (bit-identical result on
- * every rank, independent of arrival order).  One thread block, one launch; `seq` (device uint32, zero at
+ * every rank, independent of arrival order).  One launch of up to 8 independent blocks; `seq` (device uint32, zero at
  * start) counts the calls so the kernel can be replayed from a CUDA graph.  A peer that does not arrive
  * within ~2 s poisons the result with NaN instead of hanging the GPU.
  * Replaces: the gradient exchange a data-parallel run of train_poisson_nd needs after loss.backward()

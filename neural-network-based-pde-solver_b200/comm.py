@@ -29,7 +29,7 @@ class NvlinkAllReduce:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.dtype = dtype
         self.dt = L.F64 if dtype == torch.float64 else L.F32
-        self.slot = int(max_elems)
+        self.slot = (int(max_elems) + 3) // 4 * 4          # slots stay 16-byte aligned
         nbytes = C.c_size_t(0)
         L.check(lib.pde_peer_bytes(self.dt, self.slot, C.byref(nbytes)), "pde_peer_bytes")
         self._own = C.c_void_p(0)
