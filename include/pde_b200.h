@@ -205,7 +205,7 @@ int pde_keep_best(const pde_adam* cfg, const void* metric, void* best_metric, vo
 
 /* Peer-visible buffers: plain device allocations shared through CUDA IPC handles (64 bytes, exchanged by
  * the host side once at set-up).  pde_peer_bytes gives the size for a given slot capacity:
- * [signal pad | slot parity 0 | slot parity 1]; slot_elems must be a multiple of 4. */
+ * [control words | parity 0: per source rank (value, flag) pairs | parity 1]. */
 int pde_peer_bytes(int32_t dtype, int64_t slot_elems, size_t* bytes);
 int pde_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);   /* cudaMalloc + zero + cudaIpcGetMemHandle */
 int pde_peer_open(const unsigned char* handle64, void** ptr);            /* cudaIpcOpenMemHandle (another process' buffer) */
@@ -217,11 +217,12 @@ typedef struct pde_peers {
   void* base[PDE_MAX_PEERS];       /* base[r]: rank r's buffer as mapped in THIS process (own allocation at base[rank]) */
 } pde_peers;
 
-/* In-place sum of `buf` (n values) over the ranks of one box: copy-in to the rank's slot, system-scope
- * signal / wait on every peer's pad, then every rank adds all slots in rank order (bit-identical result on
- * every rank, independent of arrival order).  One launch of up to 8 independent blocks; `seq` (device uint32, zero at
- * start) counts the calls so the kernel can be replayed from a CUDA graph.  A peer that does not arrive
- * within ~2 s poisons the result with NaN instead of hanging the GPU.
+/* In-place sum of `buf` (n values) over the ranks of one box, flag-in-data push protocol: every 32-bit word
+ * is stored together with the call number as one 64-bit word into every peer's slot (one one-way NVLink trip,
+ * no fence, no separate signal); the rank then polls its own slots and adds the values in rank order
+ * (bit-identical result on every rank, independent of arrival order).  One launch; `seq` (device uint32,
+ * zero at start) counts the calls so the kernel can be replayed from a CUDA graph.  A peer that does not
+ * arrive within ~2 s poisons the result with NaN instead of hanging the GPU.
  * Replaces: the gradient exchange a data-parallel run of train_poisson_nd needs after loss.backward()
  * (Poisson_ND.py:240; the reference itself is single-device), SURVEY.md §8e. */
 int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int64_t n, int64_t slot_elems,
