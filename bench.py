@@ -162,6 +162,7 @@ def main():
     exchange = "none (one rank)"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
         # exchange step: one kernel over NVLink peer memory (pde_allreduce_oneshot); PDE_B200_EXCHANGE=nccl keeps NCCL
