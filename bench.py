@@ -104,6 +104,24 @@ def cpu_reference_rate(n_chunks, threads=None):
     return X.shape[0] / dt, dt
 
 
+def gpu_eager_reference_rate(dev, n_chunks=4):
+    """The same nested-autograd algorithm run by PyTorch eager on the B200 itself (SURVEY.md §8d's second,
+    recommended baseline): what switching the reference to `device='cuda'` gives without this library."""
+    from oracle import autograd_ref as AR
+    torch.manual_seed(0)
+    net = AR.build_mlp([DIM] + [WIDTH] * (DEPTH - 1) + [1], "sin", torch.float32).to(dev)
+    X = torch.rand(n_chunks * CPU_CHUNK, DIM, device=dev) * L_DOM
+    f = AR.manufactured_rhs(X, L_DOM, [1] * DIM)
+    AR.loss_and_grads("pinn", net, X[:CPU_CHUNK], f[:CPU_CHUNK], L_DOM, "FBC", chunk=CPU_CHUNK)  # warm-up
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    AR.loss_and_grads("pinn", net, X, f, L_DOM, "FBC", chunk=CPU_CHUNK)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return X.shape[0] / (e0.elapsed_time(e1) * 1e-3)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -307,6 +325,12 @@ def main():
             out["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
                                    "sample": f"{64 * CPU_CHUNK} of the 2^22 points (the whole step) in 2^16 chunks ({dt:.1f} s), "
                                              "oracle/autograd_ref.py (the reference's nested-autograd algorithm), fp32"}
+            try:
+                out["torch_eager_gpu_baseline"] = {
+                    "value": gpu_eager_reference_rate(dev), "unit": "points/s",
+                    "sample": f"{4 * CPU_CHUNK} points in 2^16 chunks, the same nested-autograd algorithm run by PyTorch eager on this GPU, fp32"}
+            except Exception as exc:      # reported extra, never fatal
+                out["torch_eager_gpu_baseline"] = {"value": None, "error": type(exc).__name__}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
