@@ -64,6 +64,8 @@ _LIB = None
 
 
 def lib_path():
+    if os.environ.get("PDE_B200_LIB"):   # development: an alternative build of the same library
+        return os.environ["PDE_B200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpde_b200.so")
 
 

@@ -36,8 +36,29 @@ namespace tc {
 
 constexpr int TP = 64;        // points per tile = UMMA M
 constexpr int HP = 64;        // padded hidden width = UMMA N / K
-constexpr int NEPI = 8;       // epilogue warps: quarter q = w % 4 (16 points), column half h = w / 4
+// Epilogue warps: quarter q = w % 4 (16 points), column half h = (w / 4) % 2 and, with 16 warps, row half
+// rh = w / 8: the two warps of a (q, h) pair read the same 16x256b accumulator fragments and each keeps
+// one of its two rows, so a thread carries NE = 2 instead of 4 elements per chunk (half the registers)
+// and every scheduler has four instead of two epilogue warps to hide latencies with.
+#ifndef PDE_TC_NEPI
+#define PDE_TC_NEPI 8
+#endif
+constexpr int NEPI = PDE_TC_NEPI;
+constexpr int RS = NEPI / 8;    // row split
+constexpr int NE = 4 / RS;      // elements per thread and chunk: NR rows x 2 adjacent units
+constexpr int NR = 2 / RS;      // rows per thread
+static_assert(NEPI == 8 || NEPI == 16, "8 or 16 epilogue warps");
 constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp issues the MMAs (rest idle, registers donated)
+#define PDE_TC_STR2(x) #x
+#define PDE_TC_STR(x) PDE_TC_STR2(x)
+#if PDE_TC_NEPI == 16
+#define PDE_TC_EPI_REGS 104     // 640 threads launch at 96 registers; setmaxnreg only redistributes those 61 440
+#define PDE_TC_ISS_REGS 64
+#else
+#define PDE_TC_EPI_REGS 208
+#define PDE_TC_ISS_REGS 80
+#endif
+using StashV = std::conditional<RS == 1, float4, float2>::type;   // one stashed value of a thread's NE elements
 constexpr int MAXC = 6;       // jet channels the TMEM / smem budget covers
 constexpr int COL_R0 = 0;     // TMEM columns: activation / adjoint accumulators (3 interleaved pairs)
 constexpr int COL_G = 384;    // gW accumulators: slot s at column COL_G + 64 (s / 2), lane half s % 2
@@ -96,13 +117,24 @@ __device__ __forceinline__ void sincos_cw(float z, float& s, float& c) {
   s = __uint_as_float(__float_as_uint(a) ^ ((k & 2u) << 30));
   c = __uint_as_float(__float_as_uint(b) ^ (((k + 1u) & 2u) << 30));
 }
-// `big`: warp-uniform flag "some |z| of this chunk is outside the fast range"
-__device__ __forceinline__ void act_eval(int act, float z, bool big, float& v0, float& v1) {
+// `big`: warp-uniform flag "some |z| of this chunk is outside the fast range".  One branch for all the
+// elements of a thread, so that the independent polynomial chains of the fast path are interleaved.
+template <int N>
+__device__ __forceinline__ void act_eval(int act, const float (&z)[N], bool big, float (&v0)[N], float (&v1)[N]) {
   if (act == 0) {
-    if (big) sincosf(z, &v0, &v1);
-    else sincos_cw(z, v0, v1);
+    if (big) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) sincosf(z[e], &v0[e], &v1[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < N; ++e) sincos_cw(z[e], v0[e], v1[e]);
+    }
   } else {
-    v0 = tanhf(z); v1 = 1.f - v0 * v0;
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      v0[e] = tanhf(z[e]);
+      v1[e] = 1.f - v0[e] * v0[e];
+    }
   }
 }
 
@@ -214,7 +246,7 @@ struct SmemMap {
   static constexpr int off_X = off_par + par_floats * 4;  // X tile [64][D]
   static constexpr int off_nb = off_X + 64 * D * 4;       // cotangents of the network jets [64][C]
   static constexpr int off_red = off_nb + 64 * C * 4;     // output-layer partial sums [2][64][C]
-  static constexpr int red_floats = (2 * 64 * C > 256) ? 2 * 64 * C : 256;   // also [4][64] at the end
+  static constexpr int red_floats = (2 * 64 * C > 256 * RS) ? 2 * 64 * C : 256 * RS;   // also [4 RS][64] at the end
   static constexpr int off_bar = off_red + red_floats * 4;
   static constexpr int total = off_bar + 128;
 };
@@ -239,6 +271,15 @@ __device__ __forceinline__ void stash_store(float4* p, float4 v) {
   __stcg(p, v);
 #endif
 }
+__device__ __forceinline__ void stsm_x2(uint32_t addr, uint32_t r0, uint32_t r1) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1,%2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void stash_store(float2* p, float2 v) { __stcg(p, v); }
+// stashed vector <-> the thread's element array
+__device__ __forceinline__ void to_arr(const float4& sv, float (&v)[4]) { v[0] = sv.x; v[1] = sv.y; v[2] = sv.z; v[3] = sv.w; }
+__device__ __forceinline__ void to_arr(const float2& sv, float (&v)[2]) { v[0] = sv.x; v[1] = sv.y; }
+__device__ __forceinline__ float4 from_arr(const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ float2 from_arr(const float (&v)[2]) { return make_float2(v[0], v[1]); }
 __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // UMMA descriptors as "constant high word + 14-bit start address (16-byte units) in the low word":
@@ -374,7 +415,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     // MMA issuer (warp NEPI); its warpgroup hands its registers to the epilogue.  The warp runs
     // the loops convergently and one elected lane issues, so descriptor arithmetic stays uniform.
     // =====================================================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 " PDE_TC_STR(PDE_TC_ISS_REGS) ";");
     if (warp == NEPI) {
       constexpr uint32_t ID_FWD = make_idesc(64, 64, 0, 0);   // A K-major, B K-major
       constexpr uint32_t ID_DG = make_idesc(64, 64, 0, 1);    // A K-major, B MN-major (W viewed as W^T)
@@ -532,16 +573,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     // =====================================================================================
     // epilogue warps
     // =====================================================================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    const int q = warp & 3, h = warp >> 2;
-    const int r0 = 16 * q + (lane >> 2), r1 = r0 + 8;   // this thread's two points (tile rows)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " PDE_TC_STR(PDE_TC_EPI_REGS) ";");
+    const int q = warp & 3, h = (warp >> 2) & 1, rh = warp >> 3;
+    int rows[NR];                                       // this thread's points (tile rows)
+    rows[0] = 16 * q + (lane >> 2) + (RS == 2 ? 8 * rh : 0);
+    if constexpr (NR == 2) rows[1] = rows[0] + 8;
     const int cq = 2 * (lane & 3);                      // column offset inside an 8-column block
-    // stmatrix row address of this thread: matrix i = lane/8 (hi r0-rows, hi r1-rows, lo r0-rows, lo r1-rows)
-    const int sm_row = 16 * q + 8 * ((lane >> 3) & 1) + (lane & 7);
-    const uint32_t sm_base = (uint32_t)((lane >> 4) * TILE_BYTES) + ((sm_row >> 3) << 10) + ((sm_row & 7) << 7);
+    // stmatrix row address of this thread.  8 warps: matrix i = lane/8 = (hi r0-rows, hi r1-rows, lo r0-rows,
+    // lo r1-rows); 16 warps (.x2): (hi rows, lo rows) of this warp's row half
+    const int sm_row = (RS == 1) ? 16 * q + 8 * ((lane >> 3) & 1) + (lane & 7) : 16 * q + 8 * rh + (lane & 7);
+    const int sm_tile = (RS == 1) ? (lane >> 4) : ((lane >> 3) & 1);
+    const uint32_t sm_base = (uint32_t)(sm_tile * TILE_BYTES) + ((sm_row >> 3) << 10) + ((sm_row & 7) << 7);
     const int sm_r7 = sm_row & 7;
     float* part = a.partial + (long long)blockIdx.x * a.PP;
-    float4* stash = a.stash + (long long)blockIdx.x * a.stash_f4 + warp * (NV * 32) + lane;
+    StashV* stash = reinterpret_cast<StashV*>(a.stash + (long long)blockIdx.x * a.stash_f4) + warp * (NV * 32) + lane;
+    // this thread's part of a 16x256b accumulator fragment (rows lane/4 and lane/4 + 8, two columns each);
+    // only valid after tcgen05.wait::ld
+    auto pick = [&](const float (&t)[4], float (&v)[NE]) {
+      if constexpr (RS == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = t[e];
+      } else {
+        v[0] = rh ? t[2] : t[0];
+        v[1] = rh ? t[3] : t[1];
+      }
+    };
     uint32_t ph_d = 0, ph_w = 0;
     int reg = 0;   // region the next D-consuming step reads
     bool w_pending = false;   // a bar_w commit has been issued that nobody waited for yet
@@ -555,20 +611,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     float adj_scale = 0.f;   // power-of-two scale of the adjoints of this CTA (0 = not chosen yet)
 
     // write 4 values (2 rows x 2 adjacent units) of every channel of chunk j into an operand set
-    auto pack_chunk = [&](const float (&v)[C][4], uint32_t (&pk)[C][4]) {
+    auto pack_chunk = [&](const float (&v)[C][NE], uint32_t (&pk)[C][NE]) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        split2(v[c][0], v[c][1], pk[c][0], pk[c][2]);
-        split2(v[c][2], v[c][3], pk[c][1], pk[c][3]);
+        if constexpr (RS == 1) {
+          split2(v[c][0], v[c][1], pk[c][0], pk[c][2]);
+          split2(v[c][2], v[c][3], pk[c][1], pk[c][3]);
+        } else {
+          split2(v[c][0], v[c][1], pk[c][0], pk[c][1]);
+        }
       }
     };
-    auto put_chunk = [&](uint32_t set, int j, const uint32_t (&pk)[C][4]) {
+    auto put_chunk = [&](uint32_t set, int j, const uint32_t (&pk)[C][NE]) {
       const uint32_t addr = set + sm_base + ((((2 * j + h) ^ sm_r7) & 7) << 4);
 #pragma unroll
-      for (int c = 0; c < C; ++c) stsm_x4(addr + c * 2 * TILE_BYTES, pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+      for (int c = 0; c < C; ++c) {
+        if constexpr (RS == 1) stsm_x4(addr + c * 2 * TILE_BYTES, pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+        else stsm_x2(addr + c * 2 * TILE_BYTES, pk[c][0], pk[c][1]);
+      }
     };
-    auto store_chunk = [&](uint32_t set, int j, const float (&v)[C][4]) {
-      uint32_t pk[C][4];
+    auto store_chunk = [&](uint32_t set, int j, const float (&v)[C][NE]) {
+      uint32_t pk[C][NE];
       pack_chunk(v, pk);
       put_chunk(set, j, pk);
     };
@@ -585,19 +648,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     // gradient accumulators start from zero and are added to this CTA's partial vector.  Every
     // element of `part` is owned by one thread, so the fire-and-forget adds are applied in tile order
     // (deterministic).  Precondition: bar_w of the tile's last step has been waited for.
-    float accW[3][4][4];   // running sums of gW_l: [layer slot][8-column block][fragment]
-    float accB[3][2];      // gb_l (lanes with lane % 4 == 0 of the h == 0 warps)
-    float acc0[4];         // [gW0 | gb0] fragment (h == 0 warps)
+    float accW[3][4][NE];  // running sums of gW_l: [layer slot][8-column block][fragment]
+    float accB[3][NR];     // gb_l (lanes with lane % 4 == 0 of the h == 0 warps)
+    float acc0[NE];        // [gW0 | gb0] fragment (h == 0 warps)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
       for (int b = 0; b < 4; ++b)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) accW[i][b][e] = 0.f;
-      accB[i][0] = accB[i][1] = 0.f;
+        for (int e = 0; e < NE; ++e) accW[i][b][e] = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) accB[i][r] = 0.f;
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) acc0[e] = 0.f;
+    for (int e = 0; e < NE; ++e) acc0[e] = 0.f;
     auto flush_grads = [&]() {
 #pragma unroll
       for (int sl = 0; sl < 3; ++sl) {
@@ -609,19 +673,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL + 8 * (sl + 1)), w);
           tmem_ld_wait();
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
+          for (int b = 0; b < 4; ++b) {
+            float t[NE];
+            pick(v[b], t);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) accW[sl][b][e] += v[b][e];
-          accB[sl][0] += w[0];
-          accB[sl][1] += w[2];
+            for (int e = 0; e < NE; ++e) accW[sl][b][e] += t[e];
+          }
+          float t[NE];
+          pick(w, t);
+#pragma unroll
+          for (int r = 0; r < NR; ++r) accB[sl][r] += t[2 * r];
         }
       }
       {
-        float w[4];
+        float w[4], t[NE];
         tmem_ld_16x256b(taddr_of(tmem, 32 * q + 16, COL_SMALL), w);
         tmem_ld_wait();
+        pick(w, t);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc0[e] += w[e];
+        for (int e = 0; e < NE; ++e) acc0[e] += t[e];
       }
       tc_fence_before();
     };
@@ -654,9 +724,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         }
       }
 
-      float outacc[2][C];
+      float outacc[NR][C];
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int c = 0; c < C; ++c) outacc[r][c] = 0.f;
 
@@ -670,19 +740,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           tc_fence_after();
         }
         TS(20 + l);
-        float z[C][4];   // [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]; chunk j+1 is fetched while chunk j is processed
+        float zr[C][4];  // raw accumulator fragments [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]; chunk j+1 is fetched while chunk j is processed
+        float z[C][NE];  // this thread's elements
         const uint32_t zsrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
         if constexpr (!L0) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), z[c]);
+          for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), zr[c]);
         }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;   // this thread's columns u0, u0+1
           if constexpr (L0) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int row = (e < 2) ? r0 : r1, u = u0 + (e & 1);
+            for (int e = 0; e < NE; ++e) {
+              const int row = rows[e >> 1], u = u0 + (e & 1);
               float v = sB[u];
 #pragma unroll
               for (int jd = 0; jd < D; ++jd) v = fmaf(sW0t[jd * 64 + u], sX[row * D + jd], v);
@@ -693,16 +764,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
           } else {
             if (l == 1) TS(300 + j);
+            const float b0v = sB[l * 64 + u0], b1v = sB[l * 64 + u0 + 1];   // before the wait: its "memory" clobber pins loads
             tmem_ld_wait();
             if (l == 1) TS(310 + j);
-            const float b0v = sB[l * 64 + u0], b1v = sB[l * 64 + u0 + 1];
-            z[0][0] += b0v; z[0][1] += b1v; z[0][2] += b0v; z[0][3] += b1v;
-          }
-          float av[C][4], sv0[4], sv1[4];
-          const bool big = (act == 0) && __any_sync(0xffffffffu, fmaxf(fmaxf(fabsf(z[0][0]), fabsf(z[0][1])), fmaxf(fabsf(z[0][2]), fabsf(z[0][3]))) > 32768.f);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            act_eval(act, z[0][e], big, sv0[e], sv1[e]);
+            for (int c = 0; c < C; ++c) pick(zr[c], z[c]);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) z[0][e] += (e & 1) ? b1v : b0v;
+          }
+          float av[C][NE], sv0[NE], sv1[NE];
+          float zmax = 0.f;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) zmax = fmaxf(zmax, fabsf(z[0][e]));
+          const bool big = (act == 0) && __any_sync(0xffffffffu, zmax > 32768.f);
+          act_eval<NE>(act, z[0], big, sv0, sv1);
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
             float s0, s1, s2, s3;
             act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
             av[0][e] = s0;
@@ -726,22 +803,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             const float w0v = sWL[u0], w1v = sWL[u0 + 1];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-              outacc[0][c] = fmaf(w0v, av[c][0], fmaf(w1v, av[c][1], outacc[0][c]));
-              outacc[1][c] = fmaf(w0v, av[c][2], fmaf(w1v, av[c][3], outacc[1][c]));
+#pragma unroll
+              for (int r = 0; r < NR; ++r) outacc[r][c] = fmaf(w0v, av[c][2 * r], fmaf(w1v, av[c][2 * r + 1], outacc[r][c]));
             }
           }
           if (do_bwd) {
-            stash_store(stash_at(l, j, 0), make_float4(sv0[0], sv0[1], sv0[2], sv0[3]));
-            stash_store(stash_at(l, j, 1), make_float4(sv1[0], sv1[1], sv1[2], sv1[3]));
+            stash_store(stash_at(l, j, 0), from_arr(sv0));
+            stash_store(stash_at(l, j, 1), from_arr(sv1));
             if constexpr (!L0) {
 #pragma unroll
-              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), make_float4(z[c][0], z[c][1], z[c][2], z[c][3]));
+              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), from_arr(z[c]));
             }
           }
           if (!L0 && j < 3) {
             // z has been consumed: fetch the accumulators of the next chunk now
 #pragma unroll
-            for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), z[c]);
+            for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), zr[c]);
           }
         }
         if constexpr (!L0) reg ^= 1;
@@ -752,7 +829,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 
       // ================= output layer + envelope + residual program =================
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           float v = outacc[r][c];
@@ -763,8 +840,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       if ((lane & 3) == 0) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          sRed[(h * 64 + r0) * C + c] = outacc[0][c];
-          sRed[(h * 64 + r1) * C + c] = outacc[1][c];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) sRed[(h * 64 + rows[r]) * C + c] = outacc[r][c];
         }
       }
       named_sync(1, NEPI * 32);
@@ -821,7 +898,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         // Stash of this layer (activation values, pre-activation jets) and of the layer below (whose
         // activations are this layer's wgrad operand).  Software pipeline: the registers of chunk j+1
         // are fetched as soon as chunk j has consumed them (no rotation copies).
-        float4 cur[NV], prv[NV];
+        StashV cur[NV], prv[NV];
         auto load_cur = [&](int j) {
           cur[0] = __ldcg(stash_at(l, j, 0)); cur[1] = __ldcg(stash_at(l, j, 1));
           if constexpr (LK >= 1) {
@@ -849,11 +926,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           tc_fence_after();
         }
         TS(40 + l);
-        float ab[C][4];
+        float abr[C][4];   // raw accumulator fragments
+        float ab[C][NE];
         const uint32_t absrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
         if constexpr (!TOP) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), ab[c]);
+          for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), abr[c]);
         }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
@@ -862,24 +940,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             const float w0v = sWL[u0], w1v = sWL[u0 + 1];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-              const float n0 = sNb[r0 * C + c], n1 = sNb[r1 * C + c];
-              ab[c][0] = w0v * n0; ab[c][1] = w1v * n0; ab[c][2] = w0v * n1; ab[c][3] = w1v * n1;
+#pragma unroll
+              for (int r = 0; r < NR; ++r) {
+                const float nv = sNb[rows[r] * C + c];
+                ab[c][2 * r] = w0v * nv; ab[c][2 * r + 1] = w1v * nv;
+              }
             }
           } else {
             tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < C; ++c) pick(abr[c], ab[c]);
           }
-          float zb[C][4];
+          float zb[C][NE];
           {
-            const float sv0[4] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w}, sv1[4] = {cur[1].x, cur[1].y, cur[1].z, cur[1].w};
-            float zj[C][4];   // zj[1..]: derivative channels of z (zj[0] unused)
+            float sv0[NE], sv1[NE];
+            to_arr(cur[0], sv0);
+            to_arr(cur[1], sv1);
+            float zj[C][NE];   // zj[1..]: derivative channels of z (zj[0] unused)
             if constexpr (LK >= 1) {
 #pragma unroll
-              for (int c = 1; c < C; ++c) {
-                zj[c][0] = cur[1 + c].x; zj[c][1] = cur[1 + c].y; zj[c][2] = cur[1 + c].z; zj[c][3] = cur[1 + c].w;
-              }
+              for (int c = 1; c < C; ++c) to_arr(cur[1 + c], zj[c]);
             } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+              for (int e = 0; e < NE; ++e) {
                 const int u = u0 + (e & 1);
 #pragma unroll
                 for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[i * 64 + u];
@@ -887,7 +970,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               }
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < NE; ++e) {
               float s0, s1, s2, s3;
               act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
               float t0 = s1 * ab[0][e];
@@ -910,7 +993,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               zb[0][e] = t0;
               if constexpr (TOP) {
                 // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
-                const int r = (e < 2) ? r0 : r1;
+                const int r = rows[e >> 1];
                 float g = sNb[r * C] * s0;
 #pragma unroll
                 for (int i = 0; i < ND; ++i) g = fmaf(sNb[r * C + 1 + i], s1 * zj[1 + i][e], g);
@@ -923,25 +1006,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             // ab and cur have been consumed: fetch chunk j+1
             if constexpr (!TOP) {
 #pragma unroll
-              for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), ab[c]);
+              for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), abr[c]);
             }
             load_cur(j + 1);
           }
-          uint32_t zk[C][4];
+          uint32_t zk[C][NE];
           pack_chunk(zb, zk);
-          float ap[C][4];
+          float ap[C][NE];
           if constexpr (REFILL) {
             // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
-            const float pv0[4] = {prv[0].x, prv[0].y, prv[0].z, prv[0].w}, pv1[4] = {prv[1].x, prv[1].y, prv[1].z, prv[1].w};
-            float zp[C][4];
+            float pv0[NE], pv1[NE];
+            to_arr(prv[0], pv0);
+            to_arr(prv[1], pv1);
+            float zp[C][NE];
             if constexpr (LK >= 2) {
 #pragma unroll
-              for (int c = 1; c < C; ++c) {
-                zp[c][0] = prv[1 + c].x; zp[c][1] = prv[1 + c].y; zp[c][2] = prv[1 + c].z; zp[c][3] = prv[1 + c].w;
-              }
+              for (int c = 1; c < C; ++c) to_arr(prv[1 + c], zp[c]);
             } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
+              for (int e = 0; e < NE; ++e) {
                 const int u = u0 + (e & 1);
 #pragma unroll
                 for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
@@ -949,7 +1032,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               }
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < NE; ++e) {
               float s0, s1, s2, s3;
               act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
               ap[0][e] = s0;
@@ -1006,20 +1089,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const int i0 = 32 * h + 8 * b + cq;
-            *reinterpret_cast<float2*>(gW + r0 * HP + i0) = make_float2(accW[sl][b][0] * inv, accW[sl][b][1] * inv);
-            *reinterpret_cast<float2*>(gW + r1 * HP + i0) = make_float2(accW[sl][b][2] * inv, accW[sl][b][3] * inv);
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+              *reinterpret_cast<float2*>(gW + rows[r] * HP + i0) = make_float2(accW[sl][b][2 * r] * inv, accW[sl][b][2 * r + 1] * inv);
           }
           if (h == 0 && (lane & 3) == 0) {
-            gW[HP * HP + r0] = accB[sl][0] * inv;
-            gW[HP * HP + r1] = accB[sl][1] * inv;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) gW[HP * HP + rows[r]] = accB[sl][r] * inv;
           }
         }
       }
       if (h == 0) {
         // columns cq, cq+1 of [gW0 (D cols) | gb0]
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = cq + (e & 1), o = (e < 2) ? r0 : r1;
+        for (int e = 0; e < NE; ++e) {
+          const int col = cq + (e & 1), o = rows[e >> 1];
           if (col < D) part[a.off_gW0 + o * D + col] = acc0[e] * inv;
           else if (col == D) part[a.off_gb0 + o] = acc0[e] * inv;
         }
@@ -1036,17 +1120,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           gwl[j][k] = v;
         }
       named_sync(1, NEPI * 32);
-      float* sRedW = sRed;   // [4 quarters][64 columns]
+      float* sRedW = sRed;   // [4 RS row groups][64 columns]
       if (lane < 4) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          sRedW[q * 64 + 16 * j + 8 * h + cq] = gwl[j][0];
-          sRedW[q * 64 + 16 * j + 8 * h + cq + 1] = gwl[j][1];
+          sRedW[(q + 4 * rh) * 64 + 16 * j + 8 * h + cq] = gwl[j][0];
+          sRedW[(q + 4 * rh) * 64 + 16 * j + 8 * h + cq + 1] = gwl[j][1];
         }
       }
       named_sync(1, NEPI * 32);
-      // ... then over the four quarters in fixed order
-      if (tid < 64) part[a.off_gwL + tid] = ((sRedW[tid] + sRedW[64 + tid]) + (sRedW[128 + tid] + sRedW[192 + tid])) * inv;
+      // ... then over the row groups in fixed order
+      if (tid < 64) {
+        float v = (sRedW[tid] + sRedW[64 + tid]) + (sRedW[128 + tid] + sRedW[192 + tid]);
+        if constexpr (RS == 2) v += (sRedW[256 + tid] + sRedW[320 + tid]) + (sRedW[384 + tid] + sRedW[448 + tid]);
+        part[a.off_gwL + tid] = v * inv;
+      }
       named_sync(1, NEPI * 32);
       if (tid < 64) sRed[tid] = gbl;
       named_sync(1, NEPI * 32);
@@ -1249,7 +1337,7 @@ static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl) {
   p.off_gbL = p.off_gwL + HP;
   p.PP = rup(p.off_gbL + 1, 4);
   p.n_params = (long long)p.H * p.D + p.H + (long long)(p.n_h - 1) * ((long long)p.H * p.H + p.H) + p.H + 1;
-  p.stash_f4 = (long long)p.n_h * 4 * NEPI * p.NV * 32;
+  p.stash_f4 = (long long)p.n_h * 4 * 8 * p.NV * 32;   // 16 bytes per thread of 8 warps (or 8 bytes x 16 warps)
   p.ws_params = (size_t)rup((p.D * 64 + p.n_h * 64 + 64 + 1) * 4, 256);
   p.ws_wimg = (size_t)(p.n_h - 1) * 2 * TILE_BYTES;
   p.ws_partial = (size_t)rup((long long)p.sms * p.PP * 4, 256);
