@@ -49,6 +49,9 @@ constexpr int NE = 4 / RS;      // elements per thread and chunk: NR rows x 2 ad
 constexpr int NR = 2 / RS;      // rows per thread
 static_assert(NEPI == 8 || NEPI == 16, "8 or 16 epilogue warps");
 constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp issues the MMAs (rest idle, registers donated)
+#ifndef PDE_TC_FENCE_MASK
+#define PDE_TC_FENCE_MASK 0xF   // bit j: chunk j gets its own fence + barrier arrival (bit 3 must be set)
+#endif
 #define PDE_TC_STR2(x) #x
 #define PDE_TC_STR(x) PDE_TC_STR2(x)
 #if PDE_TC_NEPI == 16
@@ -142,7 +145,7 @@ __device__ __forceinline__ void act_eval(int act, const float (&z)[N], bool big,
 // nj: network jets in, cotangents out.  Follows program_point in pde_simt.cuh with the Hessian
 // diagonal replaced by its sum.
 template <int D, int ORDER>
-__device__ void program_point_lap(const TcArgs& a, const float* x, long long gp, float (&nj)[1 + (ORDER >= 1 ? D : 0) + (ORDER == 2)],
+__device__ void program_point_lap(const TcArgs& a, const float* x, float fv, float bt, float (&nj)[1 + (ORDER >= 1 ? D : 0) + (ORDER == 2)],
                                   double (&qs)[4], double& gE) {
   constexpr int ND = (ORDER >= 1) ? D : 0;
   float b[D], b1[D], b2[D];
@@ -176,8 +179,6 @@ __device__ void program_point_lap(const TcArgs& a, const float* x, long long gp,
 #pragma unroll
     for (int i = 0; i < D; ++i) lap += 2.f * Bi[i] * nj[1 + i];
   }
-  const float fv = a.f ? a.f[gp] : 0.f;
-  const float bt = a.beta ? a.beta[gp] : a.beta_const;
   const float E = a.energy ? a.energy[0] : a.energy_const;
   const float w0 = (a.seed ? a.seed[0] : 1.f) * a.inv_n;
   float ub = 0.f, lapb = 0.f, uib[D];
@@ -635,11 +636,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       pack_chunk(v, pk);
       put_chunk(set, j, pk);
     };
+    // Chunks whose bit is clear in PDE_TC_FENCE_MASK are published together with the next chunk that has
+    // its bit set: one proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, ~200 cycles) covers several chunks.
+    int chunk_pending = 0;   // first chunk written but not yet published
     auto chunk_done = [&](int j) {
+      if (!((PDE_TC_FENCE_MASK >> j) & 1)) return;
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_chunk[j]);
+      if (lane == 0) {
+        for (int jj = chunk_pending; jj <= j; ++jj) mbar_arrive(&bar_chunk[jj]);
+      }
+      chunk_pending = (j + 1) & 3;
     };
     auto stash_at = [&](int l, int j, int v) { return stash + ((l * 4 + j) * NEPI * NV + v) * 32; };
 
@@ -696,6 +704,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       tc_fence_before();
     };
 
+    // point coordinates of the next tile, one (two for d = 5) per thread, fetched one tile ahead
+    constexpr int XR = (TP * D + NEPI * 32 - 1) / (NEPI * 32);
+    float xnext[XR];
+    auto load_x = [&](int tile) {
+#pragma unroll
+      for (int k = 0; k < XR; ++k) {
+        const int i = tid + k * NEPI * 32;
+        const long long gp = (long long)tile * TP + i / D;
+        xnext[k] = (i < TP * D && gp < a.n) ? a.X[gp * D + (i % D)] : 0.f;
+      }
+    };
+    if (tile_begin < tile_end) load_x(tile_begin);
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const long long base = (long long)tile * TP;
       TS(1);
@@ -708,11 +728,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         flush_grads();
       }
       named_sync(1, NEPI * 32);   // everyone is done with sX / sNb / sRed of the previous tile
-      for (int i = tid; i < TP * D; i += NEPI * 32) {
-        const long long gp = base + i / D;
-        sX[i] = (gp < a.n) ? a.X[gp * D + (i % D)] : 0.f;
-      }
+#pragma unroll
+      for (int k = 0; k < XR; ++k)
+        if (tid + k * NEPI * 32 < TP * D) sX[tid + k * NEPI * 32] = xnext[k];
       named_sync(1, NEPI * 32);
+      // the next tile's coordinates and this tile's coefficients are fetched now and used much later
+      if (tile + 1 < tile_end) load_x(tile + 1);
+      float fv = 0.f, bt = a.beta_const;
+      if (tid < TP && base + tid < a.n) {
+        if (a.f) fv = a.f[base + tid];
+        if (a.beta) bt = a.beta[base + tid];
+      }
       if (do_bwd) {
         for (int i = tid; i < D * 32; i += NEPI * 32) {
           const int j = i / 32, pp = 2 * (i % 32);   // row j of X^T, points pp, pp+1
@@ -852,7 +878,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         for (int c = 0; c < C; ++c) nj[c] = sRed[tid * C + c] + sRed[(64 + tid) * C + c];
         nj[0] += sWL[64];
         if (gp < a.n) {
-          program_point_lap<D, ORDER>(a, sX + tid * D, gp, nj, qs, gE);
+          program_point_lap<D, ORDER>(a, sX + tid * D, fv, bt, nj, qs, gE);
         } else {
 #pragma unroll
           for (int c = 0; c < C; ++c) nj[c] = 0.f;
