@@ -285,3 +285,63 @@ def test_qho2d_trainable_energy(dtype):
     _close(lp, g["pinn_loss"], tol)
     assert_grads_close(_grads(lin), grads_from(g, "pinn_"), tol, "qho2d energy pinn")
     _close(E_train.grad, g["pinn_gE"], tol)
+
+
+@pytest.mark.parametrize("method", ["PINN", "DRM"])
+def test_ipw2d_lbfgs_closure(method):
+    """IPW_2D.py:169-170,271-312 polishes with torch.optim.LBFGS(strong_wolfe) through a closure that
+    re-evaluates the whole loss.  The drop-in losses are ordinary autograd ops, so the same closure works on
+    them: 12 L-BFGS iterations (many closure calls each) from identical weights end at the same parameters
+    as the reference closure (nested autograd on the CPU, restated inline like the reference does), fp64."""
+    from pde_b200.schrodinger import ipw_2d as I
+    L, nx, ny = 2.0, 1, 1
+    torch.manual_seed(3)
+    ref = I.FCN([2, 16, 16, 1], nx, ny, "FBC").double()
+    ours = I.FCN([2, 16, 16, 1], nx, ny, "FBC").double()
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.cuda()
+    g = torch.linspace(0.0, L, 24, dtype=torch.float64)
+    xs, ys = torch.meshgrid(g, g, indexing="ij")
+    Xd, Yd = torch.rand(64, dtype=torch.float64) * L, torch.rand(64, dtype=torch.float64) * L
+    ud = I.Exact_solution(L, nx, ny, Xd, Yd)
+    k2 = I.k_squared(nx, ny, L)
+
+    def ref_closure_factory(opt):
+        x = xs.clone().requires_grad_(True); y = ys.clone().requires_grad_(True)
+
+        def closure():
+            opt.zero_grad()
+            u = ref(x, y, L)
+            ux = torch.autograd.grad(u, x, torch.ones_like(u), create_graph=True)[0]
+            uy = torch.autograd.grad(u, y, torch.ones_like(u), create_graph=True)[0]
+            if method == "PINN":
+                uxx = torch.autograd.grad(ux, x, torch.ones_like(ux), create_graph=True)[0]
+                uyy = torch.autograd.grad(uy, y, torch.ones_like(uy), create_graph=True)[0]
+                main = torch.mean((uxx + uyy + k2 * u) ** 2)
+            else:
+                main = torch.mean(ux ** 2 + uy ** 2) / torch.mean(u ** 2 + 1e-8)
+            total = main + 10.0 * torch.mean((ref(Xd, Yd, L) - ud) ** 2)
+            total.backward()
+            return total
+        return closure
+
+    def our_closure_factory(opt):
+        x, y = xs.cuda(), ys.cuda()
+        Xc, Yc, uc = Xd.cuda(), Yd.cuda(), ud.cuda()
+
+        def closure():
+            opt.zero_grad()
+            main = I.PINN_loss(ours, x, y, nx, ny, L) if method == "PINN" else I.DRM_loss(ours, x, y, L)
+            total = main + 10.0 * I.data_loss(ours, Xc, Yc, uc, L)
+            total.backward()
+            return total
+        return closure
+
+    finals = []
+    for model, factory in ((ref, ref_closure_factory), (ours, our_closure_factory)):
+        opt = torch.optim.LBFGS(model.parameters(), lr=0.5, max_iter=12, line_search_fn="strong_wolfe")
+        loss0 = opt.step(factory(opt))
+        finals.append((float(loss0.detach()), [p.detach().cpu().clone() for p in model.parameters()]))
+    assert abs(finals[0][0] - finals[1][0]) <= 1e-9 * max(abs(finals[0][0]), 1e-3)
+    for a, b in zip(finals[0][1], finals[1][1]):
+        assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max())), "L-BFGS trajectories diverged"
