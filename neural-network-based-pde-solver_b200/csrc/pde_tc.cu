@@ -49,6 +49,9 @@ constexpr int NE = 4 / RS;      // elements per thread and chunk: NR rows x 2 ad
 constexpr int NR = 2 / RS;      // rows per thread
 static_assert(NEPI == 8 || NEPI == 16, "8 or 16 epilogue warps");
 constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp issues the MMAs (rest idle, registers donated)
+#ifndef PDE_TC_STASH_EARLY
+#define PDE_TC_STASH_EARLY 1    // forward: stash stores at the top of the chunk instead of after its proxy fence
+#endif
 #ifndef PDE_TC_FENCE_MASK
 #define PDE_TC_FENCE_MASK 0xF   // bit j: chunk j gets its own fence + barrier arrival (bit 3 must be set)
 #endif
@@ -798,12 +801,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
             for (int e = 0; e < NE; ++e) z[0][e] += (e & 1) ? b1v : b0v;
           }
+#if PDE_TC_STASH_EARLY
+          // Stash stores first: by the time the chunk's proxy fence (whose MEMBAR waits for outstanding
+          // stores) is reached they have been acknowledged, and their source registers are free again.
+          if (do_bwd) {
+            if constexpr (!L0) {
+#pragma unroll
+              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), from_arr(z[c]));
+            }
+          }
+#endif
           float av[C][NE], sv0[NE], sv1[NE];
           float zmax = 0.f;
 #pragma unroll
           for (int e = 0; e < NE; ++e) zmax = fmaxf(zmax, fabsf(z[0][e]));
           const bool big = (act == 0) && __any_sync(0xffffffffu, zmax > 32768.f);
           act_eval<NE>(act, z[0], big, sv0, sv1);
+#if PDE_TC_STASH_EARLY
+          if (do_bwd) {
+            stash_store(stash_at(l, j, 0), from_arr(sv0));
+            stash_store(stash_at(l, j, 1), from_arr(sv1));
+          }
+#endif
 #pragma unroll
           for (int e = 0; e < NE; ++e) {
             float s0, s1, s2, s3;
@@ -833,6 +852,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int r = 0; r < NR; ++r) outacc[r][c] = fmaf(w0v, av[c][2 * r], fmaf(w1v, av[c][2 * r + 1], outacc[r][c]));
             }
           }
+#if !PDE_TC_STASH_EARLY
           if (do_bwd) {
             stash_store(stash_at(l, j, 0), from_arr(sv0));
             stash_store(stash_at(l, j, 1), from_arr(sv1));
@@ -841,6 +861,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), from_arr(z[c]));
             }
           }
+#endif
           if (!L0 && j < 3) {
             // z has been consumed: fetch the accumulators of the next chunk now
 #pragma unroll
