@@ -719,6 +719,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       }
     };
     if (tile_begin < tile_end) load_x(tile_begin);
+    bool need_flush = false;   // the gradient accumulators hold a finished tile that is not in the running sums yet
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const long long base = (long long)tile * TP;
       TS(1);
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         ph_w ^= 1;
         w_pending = false;
         tc_fence_after();
-        flush_grads();
+        need_flush = true;   // added to the running sums in the shadow of the last forward layer's GEMM (below)
       }
       named_sync(1, NEPI * 32);   // everyone is done with sX / sNb / sRed of the previous tile
 #pragma unroll
@@ -763,6 +764,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       auto fwd_layer = [&](auto l0_tag, auto last_tag, const int l) {
         constexpr bool L0 = decltype(l0_tag)::value, LAST = decltype(last_tag)::value;
         TS(10 + l);
+        if constexpr (LAST) {
+          // the previous tile's gradient accumulators: nothing writes them before this tile's reverse sweep,
+          // and the wait for this layer's GEMM below would be idle time otherwise
+          if (need_flush) {
+            flush_grads();
+            need_flush = false;
+          }
+        }
         if constexpr (!L0) {
           mbar_wait(bar_d, ph_d);
           ph_d ^= 1;
@@ -1124,8 +1133,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       mbar_wait(bar_w, ph_w);
       ph_w ^= 1;
       tc_fence_after();
-      flush_grads();
+      need_flush = true;
     }
+    if (need_flush) flush_grads();
     if (do_bwd) {
       const float inv = (adj_scale != 0.f) ? 1.f / adj_scale : 1.f;   // exact: a power of two
       // hidden GEMM layers: gW_l at slot l-1, rows o = 16 q + lane/4 (+8), columns i
