@@ -778,6 +778,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           tc_fence_after();
         }
         TS(20 + l);
+        float xr[NR][D > 0 ? D : 1];   // first layer: this thread's point coordinates (loop-invariant)
+        if constexpr (L0) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int jd = 0; jd < D; ++jd) xr[r][jd] = sX[rows[r] * D + jd];
+        }
         float zr[C][4];  // raw accumulator fragments [channel][ (r0,u0) (r0,u0+1) (r1,u0) (r1,u0+1) ]; chunk j+1 is fetched while chunk j is processed
         float z[C][NE];  // this thread's elements
         const uint32_t zsrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
@@ -791,10 +798,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           if constexpr (L0) {
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
-              const int row = rows[e >> 1], u = u0 + (e & 1);
+              const int u = u0 + (e & 1);
               float v = sB[u];
 #pragma unroll
-              for (int jd = 0; jd < D; ++jd) v = fmaf(sW0t[jd * 64 + u], sX[row * D + jd], v);
+              for (int jd = 0; jd < D; ++jd) v = fmaf(sW0t[jd * 64 + u], xr[e >> 1][jd], v);
               z[0][e] = v;
 #pragma unroll
               for (int i = 0; i < ND; ++i) z[1 + i][e] = sW0t[i * 64 + u];
@@ -982,6 +989,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           tc_fence_after();
         }
         TS(40 + l);
+        float nbr[NR][C];   // top layer: cotangents of this thread's points (loop-invariant)
+        if constexpr (TOP) {
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) nbr[r][c] = sNb[rows[r] * C + c];
+        }
         float abr[C][4];   // raw accumulator fragments
         float ab[C][NE];
         const uint32_t absrc = d_addr(reg, 0) + ((32 * q) << 16) + 8 * h;
@@ -998,7 +1012,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int c = 0; c < C; ++c) {
 #pragma unroll
               for (int r = 0; r < NR; ++r) {
-                const float nv = sNb[rows[r] * C + c];
+                const float nv = nbr[r][c];
                 ab[c][2 * r] = w0v * nv; ab[c][2 * r + 1] = w1v * nv;
               }
             }
@@ -1049,11 +1063,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               zb[0][e] = t0;
               if constexpr (TOP) {
                 // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
-                const int r = rows[e >> 1];
-                float g = sNb[r * C] * s0;
+                const int r = e >> 1;
+                float g = nbr[r][0] * s0;
 #pragma unroll
-                for (int i = 0; i < ND; ++i) g = fmaf(sNb[r * C + 1 + i], s1 * zj[1 + i][e], g);
-                if constexpr (LAP) g = fmaf(sNb[r * C + 1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
+                for (int i = 0; i < ND; ++i) g = fmaf(nbr[r][1 + i], s1 * zj[1 + i][e], g);
+                if constexpr (LAP) g = fmaf(nbr[r][1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
                 gwl[j][e & 1] += g;
               }
             }
