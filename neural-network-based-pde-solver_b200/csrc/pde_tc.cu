@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
           for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), zr[c]);
         }
-#pragma unroll 1
+#pragma unroll 2
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;   // this thread's columns u0, u0+1
           if constexpr (L0) {
