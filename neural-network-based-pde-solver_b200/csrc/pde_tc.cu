@@ -52,6 +52,9 @@ constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp 
 #ifndef PDE_TC_STASH_EARLY
 #define PDE_TC_STASH_EARLY 1    // forward: stash stores at the top of the chunk instead of after its proxy fence
 #endif
+#ifndef PDE_TC_F32X2
+#define PDE_TC_F32X2 1          // sin/cos polynomials in packed fp32 pairs (FFMA2): half the issue slots
+#endif
 #ifndef PDE_TC_FENCE_MASK
 #define PDE_TC_FENCE_MASK 0xF   // bit j: chunk j gets its own fence + barrier arrival (bit 3 must be set)
 #endif
@@ -123,6 +126,65 @@ __device__ __forceinline__ void sincos_cw(float z, float& s, float& c) {
   s = __uint_as_float(__float_as_uint(a) ^ ((k & 2u) << 30));
   c = __uint_as_float(__float_as_uint(b) ^ (((k + 1u) & 2u) << 30));
 }
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): one issue slot for two lanes' worth of math
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// sincos_cw on two arguments at once: the reduction and both polynomials in packed arithmetic (14 instead
+// of 28 FP instructions), quadrant fix-up per element.  Same operations in the same order as sincos_cw.
+__device__ __forceinline__ void sincos_cw2(float z0, float z1, float& s0, float& c0, float& s1, float& c1) {
+  const f32x2 z = pk2(z0, z1);
+  const f32x2 t = fma2(z, pk2(0.636619772f, 0.636619772f), pk2(12582912.f, 12582912.f));
+  const f32x2 kf = add2(t, pk2(-12582912.f, -12582912.f));
+  f32x2 r = fma2(kf, pk2(-1.57079601e+00f, -1.57079601e+00f), z);
+  r = fma2(kf, pk2(-3.13916473e-07f, -3.13916473e-07f), r);
+  r = fma2(kf, pk2(-5.39030253e-15f, -5.39030253e-15f), r);
+  const f32x2 r2 = mul2(r, r);
+  f32x2 sp = fma2(r2, pk2(-1.95152959e-4f, -1.95152959e-4f), pk2(8.33216087e-3f, 8.33216087e-3f));
+  sp = fma2(sp, r2, pk2(-1.66666546e-1f, -1.66666546e-1f));
+  sp = fma2(mul2(sp, r2), r, r);
+  f32x2 cp = fma2(r2, pk2(2.44331571e-5f, 2.44331571e-5f), pk2(-1.38873163e-3f, -1.38873163e-3f));
+  cp = fma2(cp, r2, pk2(4.16666457e-2f, 4.16666457e-2f));
+  cp = fma2(cp, r2, pk2(-0.5f, -0.5f));
+  cp = fma2(cp, r2, pk2(1.0f, 1.0f));
+  float t0, t1, sp0, sp1, cp0, cp1;
+  unpk2(t, t0, t1);
+  unpk2(sp, sp0, sp1);
+  unpk2(cp, cp0, cp1);
+  {
+    const uint32_t k = __float_as_uint(t0);
+    const bool odd = (k & 1u) != 0;
+    const float a = odd ? cp0 : sp0, b = odd ? sp0 : cp0;
+    s0 = __uint_as_float(__float_as_uint(a) ^ ((k & 2u) << 30));
+    c0 = __uint_as_float(__float_as_uint(b) ^ (((k + 1u) & 2u) << 30));
+  }
+  {
+    const uint32_t k = __float_as_uint(t1);
+    const bool odd = (k & 1u) != 0;
+    const float a = odd ? cp1 : sp1, b = odd ? sp1 : cp1;
+    s1 = __uint_as_float(__float_as_uint(a) ^ ((k & 2u) << 30));
+    c1 = __uint_as_float(__float_as_uint(b) ^ (((k + 1u) & 2u) << 30));
+  }
+}
 // `big`: warp-uniform flag "some |z| of this chunk is outside the fast range".  One branch for all the
 // elements of a thread, so that the independent polynomial chains of the fast path are interleaved.
 template <int N>
@@ -132,8 +194,13 @@ __device__ __forceinline__ void act_eval(int act, const float (&z)[N], bool big,
 #pragma unroll
       for (int e = 0; e < N; ++e) sincosf(z[e], &v0[e], &v1[e]);
     } else {
+      if constexpr (PDE_TC_F32X2 && N % 2 == 0) {
 #pragma unroll
-      for (int e = 0; e < N; ++e) sincos_cw(z[e], v0[e], v1[e]);
+        for (int e = 0; e < N; e += 2) sincos_cw2(z[e], z[e + 1], v0[e], v1[e], v0[e + 1], v1[e + 1]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < N; ++e) sincos_cw(z[e], v0[e], v1[e]);
+      }
     }
   } else {
 #pragma unroll
