@@ -906,18 +906,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             stash_store(stash_at(l, j, 1), from_arr(sv1));
           }
 #endif
+          if constexpr (PDE_TC_F32X2 && NE % 2 == 0 && ND >= 1) {
+            // chain rule on element pairs in packed fp32 arithmetic
 #pragma unroll
-          for (int e = 0; e < NE; ++e) {
-            float s0, s1, s2, s3;
-            act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
-            av[0][e] = s0;
-            float S = 0.f;
+            for (int e = 0; e < NE; e += 2) {
+              float s0a, s1a, s2a, s3a, s0b, s1b, s2b, s3b;
+              act_from_stash(act, sv0[e], sv1[e], s0a, s1a, s2a, s3a);
+              act_from_stash(act, sv0[e + 1], sv1[e + 1], s0b, s1b, s2b, s3b);
+              av[0][e] = s0a; av[0][e + 1] = s0b;
+              const f32x2 S1 = pk2(s1a, s1b);
+              f32x2 S;
 #pragma unroll
-            for (int i = 0; i < ND; ++i) {
-              av[1 + i][e] = s1 * z[1 + i][e];
-              S = fmaf(z[1 + i][e], z[1 + i][e], S);
+              for (int i = 0; i < ND; ++i) {
+                const f32x2 Z = pk2(z[1 + i][e], z[1 + i][e + 1]);
+                unpk2(mul2(S1, Z), av[1 + i][e], av[1 + i][e + 1]);
+                S = (i == 0) ? mul2(Z, Z) : fma2(Z, Z, S);
+              }
+              if constexpr (LAP)
+                unpk2(fma2(S1, pk2(z[1 + ND][e], z[1 + ND][e + 1]), mul2(pk2(s2a, s2b), S)), av[1 + ND][e], av[1 + ND][e + 1]);
             }
-            if constexpr (LAP) av[1 + ND][e] = fmaf(s1, z[1 + ND][e], s2 * S);
+          } else {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+              float s0, s1, s2, s3;
+              act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
+              av[0][e] = s0;
+              float S = 0.f;
+#pragma unroll
+              for (int i = 0; i < ND; ++i) {
+                av[1 + i][e] = s1 * z[1 + i][e];
+                S = fmaf(z[1 + i][e], z[1 + i][e], S);
+              }
+              if constexpr (LAP) av[1 + ND][e] = fmaf(s1, z[1 + ND][e], s2 * S);
+            }
           }
           // Operand tile first: its fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) would otherwise also wait
           // for the stash stores below to be acknowledged by L2.
