@@ -1127,39 +1127,87 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
                 if constexpr (LAP) zj[1 + ND][e] = 0.f;
               }
             }
+            if constexpr (PDE_TC_F32X2 && NE % 2 == 0 && ND >= 1) {
+              // the same recurrences on element pairs in packed fp32 arithmetic
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-              float s0, s1, s2, s3;
-              act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
-              float t0 = s1 * ab[0][e];
-              float abL = 0.f;
-              if constexpr (LAP) abL = ab[1 + ND][e];
-              float S = 0.f;
+              for (int e = 0; e < NE; e += 2) {
+                float s0a, s1a, s2a, s3a, s0b, s1b, s2b, s3b;
+                act_from_stash(act, sv0[e], sv1[e], s0a, s1a, s2a, s3a);
+                act_from_stash(act, sv0[e + 1], sv1[e + 1], s0b, s1b, s2b, s3b);
+                const f32x2 S1 = pk2(s1a, s1b), S2 = pk2(s2a, s2b);
+                f32x2 T0 = mul2(S1, pk2(ab[0][e], ab[0][e + 1]));
+                f32x2 ABL = 0, S = 0;
+                if constexpr (LAP) ABL = pk2(ab[1 + ND][e], ab[1 + ND][e + 1]);
 #pragma unroll
-              for (int i = 0; i < ND; ++i) {
-                const float zi = zj[1 + i][e];
-                t0 = fmaf(s2 * zi, ab[1 + i][e], t0);
-                S = fmaf(zi, zi, S);
-                float ti = s1 * ab[1 + i][e];
-                if constexpr (LAP) ti = fmaf(2.f * s2 * zi, abL, ti);
-                zb[1 + i][e] = ti;
-              }
-              if constexpr (LAP) {
-                t0 = fmaf(fmaf(s2, zj[1 + ND][e], s3 * S), abL, t0);
-                zb[1 + ND][e] = s1 * abL;
-              }
-              zb[0][e] = t0;
-              if constexpr (TOP) {
-                // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
-                const int r = e >> 1;
-                float g = nbr[r][0] * s0;
+                for (int i = 0; i < ND; ++i) {
+                  const f32x2 Z = pk2(zj[1 + i][e], zj[1 + i][e + 1]);
+                  const f32x2 AB = pk2(ab[1 + i][e], ab[1 + i][e + 1]);
+                  const f32x2 S2Z = mul2(S2, Z);
+                  T0 = fma2(S2Z, AB, T0);
+                  S = (i == 0) ? mul2(Z, Z) : fma2(Z, Z, S);
+                  f32x2 Ti = mul2(S1, AB);
+                  if constexpr (LAP) Ti = fma2(add2(S2Z, S2Z), ABL, Ti);
+                  unpk2(Ti, zb[1 + i][e], zb[1 + i][e + 1]);
+                }
+                if constexpr (LAP) {
+                  T0 = fma2(fma2(S2, pk2(zj[1 + ND][e], zj[1 + ND][e + 1]), mul2(pk2(s3a, s3b), S)), ABL, T0);
+                  unpk2(mul2(S1, ABL), zb[1 + ND][e], zb[1 + ND][e + 1]);
+                }
+                unpk2(T0, zb[0][e], zb[0][e + 1]);
+                if constexpr (TOP) {
+                  // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
+                  float Sa, Sb;
+                  unpk2(S, Sa, Sb);
+                  const int r = e >> 1;
+                  float ga = nbr[r][0] * s0a, gb = nbr[r][0] * s0b;
 #pragma unroll
-                for (int i = 0; i < ND; ++i) g = fmaf(nbr[r][1 + i], s1 * zj[1 + i][e], g);
-                if constexpr (LAP) g = fmaf(nbr[r][1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
-                gwl[j][e & 1] += g;
+                  for (int i = 0; i < ND; ++i) {
+                    ga = fmaf(nbr[r][1 + i], s1a * zj[1 + i][e], ga);
+                    gb = fmaf(nbr[r][1 + i], s1b * zj[1 + i][e + 1], gb);
+                  }
+                  if constexpr (LAP) {
+                    ga = fmaf(nbr[r][1 + ND], fmaf(s1a, zj[1 + ND][e], s2a * Sa), ga);
+                    gb = fmaf(nbr[r][1 + ND], fmaf(s1b, zj[1 + ND][e + 1], s2b * Sb), gb);
+                  }
+                  gwl[j][0] += ga;
+                  gwl[j][1] += gb;
+                }
               }
-            }
-          }
+            } else {
+  #pragma unroll
+              for (int e = 0; e < NE; ++e) {
+                float s0, s1, s2, s3;
+                act_from_stash(act, sv0[e], sv1[e], s0, s1, s2, s3);
+                float t0 = s1 * ab[0][e];
+                float abL = 0.f;
+                if constexpr (LAP) abL = ab[1 + ND][e];
+                float S = 0.f;
+  #pragma unroll
+                for (int i = 0; i < ND; ++i) {
+                  const float zi = zj[1 + i][e];
+                  t0 = fmaf(s2 * zi, ab[1 + i][e], t0);
+                  S = fmaf(zi, zi, S);
+                  float ti = s1 * ab[1 + i][e];
+                  if constexpr (LAP) ti = fmaf(2.f * s2 * zi, abL, ti);
+                  zb[1 + i][e] = ti;
+                }
+                if constexpr (LAP) {
+                  t0 = fmaf(fmaf(s2, zj[1 + ND][e], s3 * S), abL, t0);
+                  zb[1 + ND][e] = s1 * abL;
+                }
+                zb[0][e] = t0;
+                if constexpr (TOP) {
+                  // output-layer weight gradient: sum_c nb_c a_c with a_c recomputed from the stash
+                  const int r = e >> 1;
+                  float g = nbr[r][0] * s0;
+  #pragma unroll
+                  for (int i = 0; i < ND; ++i) g = fmaf(nbr[r][1 + i], s1 * zj[1 + i][e], g);
+                  if constexpr (LAP) g = fmaf(nbr[r][1 + ND], fmaf(s1, zj[1 + ND][e], s2 * S), g);
+                  gwl[j][e & 1] += g;
+                }
+              }
+                      }
+}
           if (j < 3) {
             // ab and cur have been consumed: fetch chunk j+1
             if constexpr (!TOP) {
@@ -1189,18 +1237,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
                 if constexpr (LAP) zp[1 + ND][e] = 0.f;
               }
             }
+            if constexpr (PDE_TC_F32X2 && NE % 2 == 0 && ND >= 1) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-              float s0, s1, s2, s3;
-              act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
-              ap[0][e] = s0;
-              float S = 0.f;
+              for (int e = 0; e < NE; e += 2) {
+                float s0a, s1a, s2a, s3a, s0b, s1b, s2b, s3b;
+                act_from_stash(act, pv0[e], pv1[e], s0a, s1a, s2a, s3a);
+                act_from_stash(act, pv0[e + 1], pv1[e + 1], s0b, s1b, s2b, s3b);
+                ap[0][e] = s0a; ap[0][e + 1] = s0b;
+                const f32x2 S1 = pk2(s1a, s1b);
+                f32x2 S = 0;
 #pragma unroll
-              for (int i = 0; i < ND; ++i) {
-                ap[1 + i][e] = s1 * zp[1 + i][e];
-                S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
+                for (int i = 0; i < ND; ++i) {
+                  const f32x2 Z = pk2(zp[1 + i][e], zp[1 + i][e + 1]);
+                  unpk2(mul2(S1, Z), ap[1 + i][e], ap[1 + i][e + 1]);
+                  S = (i == 0) ? mul2(Z, Z) : fma2(Z, Z, S);
+                }
+                if constexpr (LAP)
+                  unpk2(fma2(S1, pk2(zp[1 + ND][e], zp[1 + ND][e + 1]), mul2(pk2(s2a, s2b), S)), ap[1 + ND][e], ap[1 + ND][e + 1]);
               }
-              if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
+            } else {
+#pragma unroll
+              for (int e = 0; e < NE; ++e) {
+                float s0, s1, s2, s3;
+                act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
+                ap[0][e] = s0;
+                float S = 0.f;
+#pragma unroll
+                for (int i = 0; i < ND; ++i) {
+                  ap[1 + i][e] = s1 * zp[1 + i][e];
+                  S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
+                }
+                if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
+              }
             }
             if (j < 3) load_prv(j + 1);
           }
