@@ -323,6 +323,20 @@ def poisson_drm_loss(Ws, bs, X, f, L, bc_mode="FBC", act=SIN):
     return loss, gWs, gbs
 
 
+def mse_loss(Ws, bs, X, act, env, target=None):
+    """mean((u − target)²) (target None → mean(u²)) and its parameter gradients: the value-only terms of the
+    reference epoch — data MSE (Poisson_ND.py:230-232), one face of boundary_loss_dirichlet (:130-141)."""
+    N = X.shape[0]
+    t = 0.0 if target is None else np.asarray(target, dtype=np.float64).reshape(N, 1)
+
+    def program(U):
+        r = U[:, 0:1] - t
+        return float((r * r).mean()), 2.0 * r / N, None
+
+    loss, gWs, gbs, _ = _loss_and_grads(Ws, bs, X, act, 0, env, program)
+    return loss, gWs, gbs
+
+
 def eigen_pinn_loss(Ws, bs, X, act, env, alpha, beta, E, f=None):
     """mean((alpha·Δu + (beta−E)u − f)²), grads and dLoss/dE (R1 general)."""
     N, d = X.shape

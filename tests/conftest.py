@@ -52,16 +52,71 @@ def rel_max(a, b):
     return np.max(np.abs(a - b)) / (den if den > 0 else 1.0)
 
 
-def assert_grads_close(got, want, tol, what=""):
-    """Per-parameter-tensor relative L2 and global max-abs criteria (SURVEY.md §8d)."""
+def grads_err(got, want):
+    """Largest relative error by the two gradient criteria of SURVEY.md §8d: per-parameter-tensor relative L2
+    (for tensors that carry signal) and max-abs over the largest gradient entry.  Returns (error, where)."""
     (gW, gb), (wW, wb) = got, want
     scale = max(max(np.max(np.abs(w)) for w in wW), max(np.max(np.abs(b)) for b in wb))
+    scale = scale if scale > 0 else 1.0
+    worst, where = 0.0, ""
     for i, (a, b) in enumerate(zip(list(gW) + list(gb), list(wW) + list(wb))):
-        a = np.asarray(a, dtype=np.float64).reshape(np.asarray(b).shape)
+        b = np.asarray(b, dtype=np.float64)
+        a = np.asarray(a, dtype=np.float64).reshape(b.shape)
         nb = np.linalg.norm(b)
         if nb > 1e-3 * scale * np.sqrt(b.size):
-            assert np.linalg.norm(a - b) / nb <= tol, f"{what} tensor {i}: rel l2 {np.linalg.norm(a - b) / nb:.3e} > {tol}"
-        assert np.max(np.abs(a - b)) <= tol * scale, f"{what} tensor {i}: max abs {np.max(np.abs(a - b)):.3e} > {tol}*{scale:.3e}"
+            e = np.linalg.norm(a - b) / nb
+            if not e <= worst:
+                worst, where = e, f"tensor {i} rel l2"
+        e = np.max(np.abs(a - b)) / scale
+        if not e <= worst:
+            worst, where = e, f"tensor {i} max abs"
+    return worst, where
+
+
+def assert_grads_close(got, want, tol, what=""):
+    """Per-parameter-tensor relative L2 and global max-abs criteria (SURVEY.md §8d)."""
+    e, where = grads_err(got, want)
+    assert e <= tol, f"{what} {where}: {e:.3e} > {tol:.3e}"
+
+
+# ---- parity bars.  north_star: 1e-5 relative in fp32, 1e-10 in fp64, against the reference's float64 outputs.
+# A float32 bar may be raised ONLY to twice the distance between the reference's own float32 run and its
+# float64 run on the same fixture (stored by make_golden.py as ref32_*): where the reference's fp32 arithmetic
+# is itself further than 5e-6 from its fp64 result, no fp32 implementation can be asked to do better.
+# float64 bars are never raised: the stored conditioning figures (c64_*, <= 3e-14 on every fixture) show that a
+# 1-ulp change of the inputs moves no output by more than 3e-14 relative.
+BASE_TOL = {"float32": 1e-5, "float64": 1e-10}
+
+
+def _dt(dtype):
+    return str(dtype).replace("torch.", "")
+
+
+def loss_bar(g, key, dtype):
+    base = BASE_TOL[_dt(dtype)]
+    if _dt(dtype) == "float64" or ("ref32_" + key) not in g:
+        return base
+    want = float(g[key])
+    return max(base, 2.0 * abs(float(g["ref32_" + key]) - want) / max(abs(want), 1e-3))
+
+
+def grads_bar(g, prefix, dtype):
+    base = BASE_TOL[_dt(dtype)]
+    if _dt(dtype) == "float64" or ("ref32_" + prefix + "gW0") not in g:
+        return base
+    e, _ = grads_err(grads_from(g, "ref32_" + prefix), grads_from(g, prefix))
+    return max(base, 2.0 * e)
+
+
+def assert_loss_close(got, g, key, dtype, what=""):
+    got = float(got.detach()) if hasattr(got, "detach") else float(got)
+    want, tol = float(g[key]), loss_bar(g, key, dtype)
+    e = abs(got - want) / max(abs(want), 1e-3)
+    assert e <= tol, f"{what} {key}: {got!r} vs {want!r}: {e:.3e} > {tol:.3e}"
+
+
+def assert_grads_golden(got, g, prefix, dtype, what=""):
+    assert_grads_close(got, grads_from(g, prefix), grads_bar(g, prefix, dtype), f"{what} {prefix}")
 
 
 @pytest.fixture(scope="session")

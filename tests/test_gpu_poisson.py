@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_grads_close, grads_from, load_golden, net_from
+from conftest import (assert_grads_close, assert_grads_golden, assert_loss_close, grads_from, load_golden, net_from)
 
 pytestmark = pytest.mark.gpu
 
@@ -116,17 +116,87 @@ def test_poisson_wan_vs_reference_golden():
         vm = _model_from(pb, g, None, dtype, "v_", cls=pb.poisson.CriticNet)
         X = torch.tensor(g["X"], dtype=dtype, device="cuda", requires_grad=True)
         f = torch.tensor(g["f"], dtype=dtype, device="cuda")
-        tol = TOL[dtype]
         lu, lv, weak, pn = pb.poisson.wan_losses(um, vm, X, f, float(g["L"]), v_reg_weight=float(g["v_reg_weight"]))
         for got, key in ((lu, "loss_u"), (lv, "loss_v"), (weak, "weak"), (pn, "phi_norm")):
-            assert abs(got.item() - g[key]) <= 4 * tol * max(abs(g[key]), 1e-3), key
+            assert_loss_close(got, g, key, dtype, "poisson wan")
         lu.backward(retain_graph=True)
-        assert_grads_close(_grads_of(um), grads_from(g, "lu_u_"), 4 * tol, "lu/u")
-        assert_grads_close(_grads_of(vm), grads_from(g, "lu_v_"), 4 * tol, "lu/v")
+        assert_grads_golden(_grads_of(um), g, "lu_u_", dtype)
+        assert_grads_golden(_grads_of(vm), g, "lu_v_", dtype)
         um.zero_grad(); vm.zero_grad()
         lv.backward()
-        assert_grads_close(_grads_of(um), grads_from(g, "lv_u_"), 4 * tol, "lv/u")
-        assert_grads_close(_grads_of(vm), grads_from(g, "lv_v_"), 4 * tol, "lv/v")
+        assert_grads_golden(_grads_of(um), g, "lv_u_", dtype)
+        assert_grads_golden(_grads_of(vm), g, "lv_v_", dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_value_terms_vs_reference_golden(dtype):
+    """The value-only terms of the reference epoch (Poisson_ND.py:130-147,230-239) on the points the fixture
+    stores: data MSE (data_loss), both norm_loss modes on u from the order-0 jet kernel, and the Dirichlet face
+    penalty face by face (what boundary_loss_dirichlet evaluates on its own draws)."""
+    import pde_b200 as pb
+    g = load_golden("poisson_value_terms_d3_w16_rb")
+    L = float(g["L"])
+    m = _model_from(pb, g, "RB", dtype)
+    Xd = torch.tensor(g["Xd"], dtype=dtype, device="cuda")
+    ud = torch.tensor(g["ud"], dtype=dtype, device="cuda")
+    ld = pb.poisson.data_loss(m, Xd, ud, L); ld.backward()
+    assert_loss_close(ld, g, "data_loss", dtype)
+    assert_grads_golden(_grads_of(m), g, "data_", dtype)
+    for mode in ("nontrivial", "l2"):
+        m.zero_grad()
+        u = pb.poisson.solution_jets(m, Xd, L, 0)[0]
+        ln = pb.poisson.norm_loss(u, mode=mode); ln.backward()
+        assert_loss_close(ln, g, f"norm_{mode}_loss", dtype)
+        assert_grads_golden(_grads_of(m), g, f"norm_{mode}_", dtype)
+    with pytest.raises(ValueError):
+        pb.poisson.norm_loss(u, mode="xx")
+    m.zero_grad()
+    Xb = torch.tensor(g["Xb"], dtype=dtype, device="cuda")
+    lb = sum(pb.poisson.data_loss(m, xb, None, L) for xb in Xb) / Xb.shape[0]
+    lb.backward()
+    assert_loss_close(lb, g, "bc_loss", dtype)
+    assert_grads_golden(_grads_of(m), g, "bc_", dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("dim,bc", [(2, "RB"), (3, "FBC"), (5, "RB")])
+def test_boundary_loss_dirichlet_vs_oracle(dim, bc, dtype):
+    """boundary_loss_dirichlet draws its 2d face batches from the device generator (Poisson_ND.py:130-141: the
+    global RNG there).  Re-seeding replays the draws, and the numpy oracle evaluates mean over faces of mean(u^2)
+    and its parameter gradient on exactly those points."""
+    import pde_b200 as pb
+    from oracle import jets_numpy as O
+    L, Nb = 2.0, 37
+    torch.manual_seed(11 + dim)
+    m = pb.poisson.SolutionNet(dim, 24, 4, bc).to("cuda", dtype)
+    torch.manual_seed(5)
+    lb = pb.poisson.boundary_loss_dirichlet(m, L, Nb, dim, "cuda")
+    lb.backward()
+    torch.manual_seed(5)
+    faces = []
+    for i in range(dim):
+        for at_L in (False, True):
+            X = torch.rand(Nb, dim, device="cuda", dtype=dtype) * L
+            X[:, i] = L if at_L else 0.0
+            faces.append(X.double().cpu().numpy())
+    lin = [x for x in m.net if isinstance(x, torch.nn.Linear)]
+    Ws = [l.weight.detach().double().cpu().numpy() for l in lin]
+    bs = [l.bias.detach().double().cpu().numpy() for l in lin]
+    env = dict(kind=O.ENV_POLY if bc == "FBC" else O.ENV_NONE, lo=0.0, hi=L)
+    want, gW, gb = 0.0, [np.zeros_like(W) for W in Ws], [np.zeros_like(b) for b in bs]
+    for X in faces:
+        l, gWs, gbs = O.mse_loss(Ws, bs, X, O.SIN, env, None)
+        want += l / len(faces)
+        for a, b in zip(gW, gWs):
+            a += b / len(faces)
+        for a, b in zip(gb, gbs):
+            a += b / len(faces)
+    tol = TOL[dtype]
+    if bc == "FBC":   # the envelope vanishes on every face: the term and its gradient are exactly zero
+        assert abs(lb.item()) <= 1e-12 and want == 0.0
+    else:
+        assert abs(lb.item() - want) <= tol * abs(want), (lb.item(), want)
+        assert_grads_close(_grads_of(m), (gW, gb), tol, f"bc d{dim}")
 
 
 def test_chunk_linearity_and_ragged_sizes():
