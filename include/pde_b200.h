@@ -141,6 +141,22 @@ int pde_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pd
  * 0 = generic SIMT FMA kernel, 1 = tcgen05 tensor-core kernel; negative = pde_status. Pure query. */
 int pde_query_path(const pde_net* net, const pde_program* prog, int64_t n_points);
 
+/* Same query for pde_jets_forward / pde_jets_backward (orders 0 and 1 run on the tcgen05 kernel for fp32 networks
+ * [d, H<=64, ...] above 4096 points, e.g. both networks of wan_losses at n_interior points, Poisson_ND.py:105-128). */
+int pde_query_jets_path(const pde_net* net, int32_t order, int64_t n_points);
+
+/* Kernel-family override, process wide: -1 automatic (default; initial value from PDE_B200_PATH=simt|tc, read once),
+ * 0 generic SIMT kernel always, 1 tcgen05 kernel for every shape it implements regardless of the point count.
+ * The parity tests use it to run both families on identical inputs.  There is no reference counterpart. */
+int pde_set_kernel_path(int32_t path);
+int pde_kernel_path(void);
+
+/* Which family the calling thread's last fused / jets call actually launched (0 SIMT, 1 tcgen05, -1 none yet), and
+ * how many kernels this library has enqueued in the process so far (every launch site counts itself).  Host-side
+ * bookkeeping for bench.py's `kernel_path` and `gpu_launches` fields; no reference counterpart. */
+int pde_last_kernel_path(void);
+uint64_t pde_launch_count(void);
+
 /* WAN weak-form coupling of two networks on their jets (order 1), elementwise.
  * Replaces: bump_w + wan_losses (Poisson_ND.py:74-88,105-128), function_w + WAN_loss
  * (IPW_1D_WAN.py:31-59,88-115; QHO_2D.py:172-225), weight_fn_w + wan_loss (KH_1D.py:138-148,244-269).

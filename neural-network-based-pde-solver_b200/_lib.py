@@ -19,7 +19,8 @@ EXPORTS = [
     "pde_program_order", "pde_workspace_bytes", "pde_jets_forward", "pde_jets_backward",
     "pde_residual_loss_grad", "pde_wan_pointwise", "pde_query_path", "pde_sample_points_rhs", "pde_adam_step",
     "pde_keep_best", "pde_peer_bytes", "pde_peer_alloc", "pde_peer_open", "pde_peer_close", "pde_peer_free",
-    "pde_allreduce_oneshot",
+    "pde_allreduce_oneshot", "pde_query_jets_path", "pde_set_kernel_path", "pde_kernel_path", "pde_last_kernel_path",
+    "pde_launch_count",
 ]
 MAX_PEERS = 8
 
@@ -104,9 +105,12 @@ def load():
     lib.pde_peer_close.argtypes = [vp]
     lib.pde_peer_free.argtypes = [vp]
     lib.pde_allreduce_oneshot.argtypes = [C.POINTER(Peers), i32, vp, i64, i64, vp, vp]
+    lib.pde_query_jets_path.argtypes = [C.POINTER(Net), i32, i64]
+    lib.pde_set_kernel_path.argtypes = [i32]
     for name in EXPORTS:
-        if name not in ("pde_strerror",):
+        if name not in ("pde_strerror", "pde_launch_count"):
             getattr(lib, name).restype = C.c_int
+    lib.pde_launch_count.restype = C.c_uint64
     if lib.pde_abi_version() != 1:
         raise PdeError("libpde_b200.so ABI version mismatch")
     _LIB = lib

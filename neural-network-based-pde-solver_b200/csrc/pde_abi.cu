@@ -6,9 +6,18 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/pde_b200.h"
 #include "pde_launch.h"
 #include "pde_tc.h"
+
+namespace pde {
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local int g_last_path = -1;
+void count_launch(int k) { g_launches.fetch_add((unsigned long long)k, std::memory_order_relaxed); }
+void set_last_path(int path) { g_last_path = path; }
+}  // namespace pde
 
 namespace {
 
@@ -227,6 +236,7 @@ int run_net(const pde_net* net, int order, int mode, const pde_envelope* env, co
   a.partial = partial; a.psums = psums; a.PP = p.PP;
   a.off_gW0 = p.off_gW0; a.off_gb0 = p.off_gb0; a.off_gW = p.off_gW; a.off_gwL = p.off_gwL; a.off_gbL = p.off_gbL;
   if (launch_net<T>(p.D, order, p.grid, p.nthreads, p.smem_bytes, st, a) != cudaSuccess) return PDE_ERR_CUDA;
+  set_last_path(0);
 
   if (mode == MODE_JETS_FWD) return PDE_OK;
   ReduceArgs<T> r;
@@ -308,6 +318,8 @@ int pde_jets_forward(const pde_net* net, int32_t order, const void* X, int64_t n
                      void* workspace, size_t workspace_bytes, void* stream) {
   if (!net || !J) return PDE_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = pde::tc_jets_forward(net, order, X, n_points, J, workspace, workspace_bytes, st);
+  if (rc != PDE_ERR_UNSUPPORTED) return rc;
   if (net->dtype == PDE_F64)
     return run_net<double>(net, order, MODE_JETS_FWD, nullptr, nullptr, X, n_points, nullptr, 1.0, J, nullptr, nullptr,
                            nullptr, nullptr, workspace, workspace_bytes, st);
@@ -319,6 +331,8 @@ int pde_jets_backward(const pde_net* net, int32_t order, const void* X, int64_t 
                       void* grad, void* workspace, size_t workspace_bytes, void* stream) {
   if (!net || !Jbar || !grad) return PDE_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = pde::tc_jets_backward(net, order, X, n_points, Jbar, grad, workspace, workspace_bytes, st);
+  if (rc != PDE_ERR_UNSUPPORTED) return rc;
   if (net->dtype == PDE_F64)
     return run_net<double>(net, order, MODE_JETS_BWD, nullptr, nullptr, X, n_points, nullptr, 1.0, nullptr, Jbar,
                            nullptr, grad, nullptr, workspace, workspace_bytes, st);
@@ -354,6 +368,24 @@ int pde_query_path(const pde_net* net, const pde_program* prog, int64_t n_points
   if (!prog) return PDE_ERR_INVALID;
   return pde::tc_supported(net, prog, n_points) ? 1 : 0;
 }
+
+int pde_query_jets_path(const pde_net* net, int32_t order, int64_t n_points) {
+  int st = validate_net(net);
+  if (st) return st;
+  return pde::tc_jets_supported(net, order, n_points) ? 1 : 0;
+}
+
+int pde_set_kernel_path(int32_t path) {
+  if (path < -1 || path > 1) return PDE_ERR_INVALID;
+  pde::tc_set_path_override(path);
+  return PDE_OK;
+}
+
+int pde_kernel_path(void) { return pde::tc_get_path_override(); }
+
+int pde_last_kernel_path(void) { return pde::g_last_path; }
+
+uint64_t pde_launch_count(void) { return pde::g_launches.load(std::memory_order_relaxed); }
 
 int pde_wan_pointwise(const pde_wan* wan, const void* X, int64_t n_points, const void* Ju, const void* Jv,
                       const void* seed, double inv_n, void* sums, void* Jbar_u, void* Jbar_v, void* workspace,

@@ -27,6 +27,8 @@
 
 #include "../../include/pde_b200.h"
 
+namespace pde { void count_launch(int k); }   // pde_abi.cu: launch counter behind pde_launch_count()
+
 namespace {
 
 constexpr int CTRL_BYTES = 512;     // local control words (block-completion counter) in front of the slots
@@ -204,6 +206,7 @@ int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int6
   const int grid = (int)(g < 1 ? 1 : (g > COMM_MAX_BLOCKS ? COMM_MAX_BLOCKS : g));
   if (dtype == PDE_F32) allreduce_oneshot_kernel<float><<<grid, COMM_THREADS, 0, st>>>(a);
   else allreduce_oneshot_kernel<double><<<grid, COMM_THREADS, 0, st>>>(a);
+  pde::count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PDE_OK : PDE_ERR_CUDA;
 }
 

@@ -51,6 +51,7 @@ static cudaError_t launch_net_impl(int dim, int order, int grid, int block, size
     if (err == cudaSuccess) {
       net_kernel<T, D, O><<<grid, block, smem, st>>>(a);
       err = cudaGetLastError();
+      count_launch();
     }
   });
   return err;
@@ -171,6 +172,7 @@ static cudaError_t launch_wan_impl(cudaStream_t st, const WanArgs<T>& a) {
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return err;
   wan_finish_kernel<T><<<1, 32, 0, st>>>(a.psums, a.blocks, a.sums);
+  count_launch(2);
   return cudaGetLastError();
 }
 
@@ -179,6 +181,7 @@ static cudaError_t launch_pack_impl(cudaStream_t st, const PackArgs<T>& a) {
   int blocks = (int)((a.total + 255) / 256);
   if (blocks > 1184) blocks = 1184;
   pack_kernel<T><<<blocks, 256, 0, st>>>(a);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -187,6 +190,7 @@ static cudaError_t launch_reduce_impl(cudaStream_t st, const ReduceArgs<T>& a) {
   long long total = a.n_params + a.n_q + 1;
   int blocks = (int)((total + 127) / 128);
   reduce_kernel<T><<<blocks, 128, 0, st>>>(a);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -6,6 +6,11 @@
 
 namespace pde {
 
+// Process-wide counters the host side reads through the C ABI (pde_launch_count, pde_last_kernel_path): every kernel
+// this library enqueues is counted where it is launched, and the fused calls record which kernel family served them.
+void count_launch(int k = 1);
+void set_last_path(int path);   // 0 generic SIMT kernel, 1 tcgen05 kernel
+
 struct KernelInfo {
   const void* fn;
   int regs;

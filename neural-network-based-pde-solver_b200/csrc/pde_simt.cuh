@@ -529,9 +529,11 @@ __global__ void net_kernel(const KArgs<T> a) {
           part[a.off_gwL + uo] += g;
         }
         if (tid == 0) {
-          T g = T(0);
-          for (int pp = 0; pp < P; ++pp) g += s.out[pp * C];
-          part[a.off_gbL] += g;
+          // bias gradients are plain sums of signed cotangents over the points (for WAN critics they cancel to a
+          // small remainder): summed in double so that the result carries the rounding of the terms only
+          double g = 0.0;
+          for (int pp = 0; pp < P; ++pp) g += (double)s.out[pp * C];
+          part[a.off_gbL] += (T)g;
         }
       } else {
         const T* Zb = s.Z + (long long)(l + 1) * P * pitchP;
@@ -569,9 +571,9 @@ __global__ void net_kernel(const KArgs<T> a) {
         }
         T* gb = gW + (long long)Hp * Hp;
         for (int o = tid; o < Hp; o += nt) {
-          T g = T(0);
-          for (int pp = 0; pp < P; ++pp) g += Zb[(long long)pp * pitchP + o];
-          gb[o] += g;
+          double g = 0.0;
+          for (int pp = 0; pp < P; ++pp) g += (double)Zb[(long long)pp * pitchP + o];
+          gb[o] += (T)g;
         }
       }
       __syncthreads();
@@ -588,9 +590,9 @@ __global__ void net_kernel(const KArgs<T> a) {
       part[a.off_gW0 + i] += g;
     }
     for (int o = tid; o < Hp; o += nt) {
-      T g = T(0);
-      for (int pp = 0; pp < P; ++pp) g += s.Z[(long long)pp * pitchP + o];
-      part[a.off_gb0 + o] += g;
+      double g = 0.0;
+      for (int pp = 0; pp < P; ++pp) g += (double)s.Z[(long long)pp * pitchP + o];
+      part[a.off_gb0 + o] += (T)g;
     }
     __syncthreads();
   }

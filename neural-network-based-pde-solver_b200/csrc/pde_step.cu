@@ -15,6 +15,8 @@
 
 #include "../../include/pde_b200.h"
 
+namespace pde { void count_launch(int k); }   // pde_abi.cu: launch counter behind pde_launch_count()
+
 namespace {
 
 // ---------------------------------------------------------------- Philox4x32-10 (counter-based, stateless)
@@ -202,6 +204,7 @@ int pde_sample_points_rhs(int32_t dtype, int32_t dim, int64_t n_points, double l
   const int block = 256, grid = grid_for(n_points, block);
   if (dtype == PDE_F32) sample_rhs_kernel<float><<<grid, block, 0, st>>>(a);
   else sample_rhs_kernel<double><<<grid, block, 0, st>>>(a);
+  pde::count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PDE_OK : PDE_ERR_CUDA;
 }
 
@@ -229,6 +232,7 @@ int pde_adam_step(const pde_adam* cfg, const void* grad_flat, void* exp_avg, voi
   else adam_kernel<double><<<grid, block, 0, st>>>(a);
   if (cudaGetLastError() != cudaSuccess) return PDE_ERR_CUDA;
   bump_step_kernel<<<1, 1, 0, st>>>(static_cast<long long*>(step));
+  pde::count_launch(2);
   return cudaGetLastError() == cudaSuccess ? PDE_OK : PDE_ERR_CUDA;
 }
 
@@ -252,6 +256,7 @@ int pde_keep_best(const pde_adam* cfg, const void* metric, void* best_metric, vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cfg->dtype == PDE_F32) keep_best_kernel<float><<<1, 1024, 0, st>>>(a);
   else keep_best_kernel<double><<<1, 1024, 0, st>>>(a);
+  pde::count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PDE_OK : PDE_ERR_CUDA;
 }
 

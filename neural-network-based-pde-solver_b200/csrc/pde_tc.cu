@@ -25,6 +25,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <type_traits>
 
 #include "pde_launch.h"
@@ -92,6 +93,9 @@ struct TcArgs {
   float4* stash;                // [grid][stash_f4]
   long long PP, stash_f4, off_gW0, off_gb0, off_gW, off_gwL, off_gbL;
   long long* dbg;               // timeline buffer (builds with -DPDE_TC_TIMELINE only), else null
+  int mode;                     // 0: envelope + residual program; 1: network jets out (forward only); 2: jet cotangents in
+  float* J;                     // mode 1: (n, C) network jets (value, first derivatives) out
+  const float* Jbar;            // mode 2: (n, C) cotangents of the network jets in
 };
 
 // ---------------------------------------------------------------- per-element math
@@ -418,6 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   uint64_t* bar_own = bar_chunk + 6;   // issuer-private: "everything I issued so far has completed"
   uint64_t* bar_wt = bar_chunk + 7;    // bulk copy of a W tile pair has landed (non-resident W only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_chunk + 8);
+  float* sMx = reinterpret_cast<float*>(bar_chunk + 10);   // per-tile maximum cotangent of warps 0 and 1
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_h = a.n_h;
@@ -679,7 +684,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) gwl[j][0] = gwl[j][1] = 0.f;
     float gbl = 0.f;   // output bias gradient partial (program threads)
-    float adj_scale = 0.f;   // power-of-two scale of the adjoints of this CTA (0 = not chosen yet)
+    float adj_scale = 0.f;   // power-of-two scale the running gradient sums carry (0 = not chosen yet)
+    float cur_scale = 1.f;   // scale of the current tile's adjoints
 
     // write 4 values (2 rows x 2 adjacent units) of every channel of chunk j into an operand set
     auto pack_chunk = [&](const float (&v)[C][NE], uint32_t (&pk)[C][NE]) {
@@ -1002,45 +1008,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int c = 0; c < C; ++c) nj[c] = sRed[tid * C + c] + sRed[(64 + tid) * C + c];
         nj[0] += sWL[64];
-        if (gp < a.n) {
-          program_point_lap<D, ORDER>(a, sX + tid * D, fv, bt, nj, qs, gE);
-        } else {
+        bool programmed = false;
+        if constexpr (ORDER <= 1) {
+          // jet modes (pde_jets_forward / pde_jets_backward): for order <= 1 the kernel's channels are the ABI's
+          if (a.mode == 1) {
+            if (gp < a.n) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) nj[c] = 0.f;
+              for (int c = 0; c < C; ++c) a.J[gp * C + c] = nj[c];
+            }
+            programmed = true;
+          } else if (a.mode == 2) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) nj[c] = (gp < a.n) ? a.Jbar[gp * C + c] : 0.f;
+            programmed = true;
+          }
+        }
+        if (!programmed) {
+          if (gp < a.n) {
+            program_point_lap<D, ORDER>(a, sX + tid * D, fv, bt, nj, qs, gE);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) nj[c] = 0.f;
+          }
         }
       }
       TS(2);
       if (!do_bwd) continue;
-      if (adj_scale == 0.f) {
-        // Power-of-two scale of this CTA's adjoints, from its first tile: the largest network-jet
-        // cotangent becomes 2..4, which keeps the 16-bit operand splits of the reverse sweep well
-        // inside their range whatever the size of the residual; undone when the gradients are written.
-        named_sync(1, NEPI * 32);   // sRed has been read
+      // Power-of-two scale of the adjoints, re-derived from every tile's largest network-jet cotangent and kept
+      // while that maximum times the scale stays inside [2^-4, 2^8]: the 16-bit operand splits of the reverse
+      // sweep then sit well inside the fp16 range whatever the size of the residual and however it drifts over
+      // the CTA's tiles.  When the scale has to move, the running fp32 gradient sums are multiplied by the exact
+      // power-of-two ratio (the previous tile's TMEM accumulators were flushed into them during this tile's last
+      // forward layer), so the sums always carry the current scale; it is undone when the gradients are written.
+      {
         float mx = 0.f;
         if (tid < TP) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) mx = fmaxf(mx, fabsf(nj[c]));
-        }
+          for (int c = 0; c < C; ++c) {
+            mx = fmaxf(mx, fabsf(nj[c]));
+            sNb[tid * C + c] = nj[c];
+          }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) sRed[warp] = mx;
+          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (lane == 0) sMx[warp] = mx;
+        }
         named_sync(1, NEPI * 32);
-        mx = fmaxf(sRed[0], sRed[1]);
-        int ex = 0;
-        if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &ex);
-        ex = max(-100, min(100, ex));
-        adj_scale = (mx > 0.f && mx < 3.0e38f) ? ldexpf(1.f, 2 - ex) : 1.f;
-      }
-      if (tid < TP) {
+        mx = fmaxf(sMx[0], sMx[1]);
+        const float sm = adj_scale * mx;
+        if (mx > 1e-30f && mx < 3.0e38f && (adj_scale == 0.f || sm > 256.f || sm < 0.0625f)) {
+          int ex = (int)((__float_as_uint(mx) >> 23) & 255u) - 126;       // mx = m 2^ex, m in [0.5, 1)
+          ex = max(-60, min(60, ex));
+          const float ns = __uint_as_float((uint32_t)(127 + 2 - ex) << 23);   // largest cotangent -> [2, 4)
+          if (adj_scale != 0.f) {
+            const float ratio = ns / adj_scale;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          nj[c] *= adj_scale;
-          sNb[tid * C + c] = nj[c];
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int e = 0; e < NE; ++e) accW[i][b][e] *= ratio;
+#pragma unroll
+              for (int r = 0; r < NR; ++r) accB[i][r] *= ratio;
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) acc0[e] *= ratio;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { gwl[j][0] *= ratio; gwl[j][1] *= ratio; }
+            gbl *= ratio;
+          }
+          adj_scale = ns;
         }
-        gbl += nj[0];
+        cur_scale = (adj_scale != 0.f) ? adj_scale : 1.f;   // all cotangents so far are zero: nothing to scale
+        if (tid < TP) gbl += nj[0] * cur_scale;
       }
-      named_sync(1, NEPI * 32);
-      if (!do_bwd) continue;
 
       // ================= reverse sweep =================
       auto bwd_layer = [&](auto top_tag, auto lk_tag, const int l) {
@@ -1082,7 +1122,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
           for (int r = 0; r < NR; ++r)
 #pragma unroll
-            for (int c = 0; c < C; ++c) nbr[r][c] = sNb[rows[r] * C + c];
+            for (int c = 0; c < C; ++c) nbr[r][c] = sNb[rows[r] * C + c] * cur_scale;
         }
         float abr[C][4];   // raw accumulator fragments
         float ab[C][NE];
@@ -1487,10 +1527,18 @@ static cudaError_t launch_tc(const TcPlan& p, const TcArgs& a, cudaStream_t st) 
   return a.act == PDE_ACT_TANH ? launch_act<1>(p, a, st) : launch_act<0>(p, a, st);
 }
 
+// Kernel-family override: -1 automatic (tensor-core kernel where supported), 0 generic SIMT kernel, 1 tensor-core
+// kernel also below its size threshold.  Initial value from PDE_B200_PATH=simt|tc, read once; pde_set_kernel_path
+// changes it (parity tests run both families on the same inputs).
+static std::atomic<int> g_path_override{-2};
 static int path_override() {
-  // PDE_B200_PATH=simt|tc forces one kernel family (used by the parity tests); default: tc where supported
-  const char* e = getenv("PDE_B200_PATH");
-  return !e ? -1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc") == 0 ? 1 : -1));
+  int v = g_path_override.load(std::memory_order_relaxed);
+  if (v == -2) {
+    const char* e = getenv("PDE_B200_PATH");
+    v = !e ? -1 : (strcmp(e, "simt") == 0 ? 0 : (strcmp(e, "tc") == 0 ? 1 : -1));
+    g_path_override.store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 #ifdef PDE_TC_TIMELINE
@@ -1538,18 +1586,21 @@ static bool shape_ok(const pde_net* net, int order, long long n) {
 
 static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl) {
   if (!shape_ok(net, order, n)) return PDE_ERR_UNSUPPORTED;
-  static int sms_cached = 0;
-  if (!sms_cached) {
-    int dev = 0, sms = 0, cc = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return PDE_ERR_NO_DEVICE; }
+  static std::atomic<int> sms_cached[64];   // per device ordinal
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return PDE_ERR_NO_DEVICE; }
+  int sms_dev = sms_cached[dev].load(std::memory_order_relaxed);
+  if (!sms_dev) {
+    int sms = 0, cc = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return PDE_ERR_NO_DEVICE;
     if (cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return PDE_ERR_NO_DEVICE;
     if (cc != 10) return PDE_ERR_UNSUPPORTED;
-    sms_cached = sms;
+    sms_cached[dev].store(sms, std::memory_order_relaxed);
+    sms_dev = sms;
   }
   TcPlan& p = *pl;
   memset(&p, 0, sizeof(p));
-  p.sms = sms_cached;
+  p.sms = sms_dev;
   p.D = net->dim; p.order = order;
   p.C = 1 + (order >= 1 ? p.D : 0) + (order == 2);
   p.NV = 1 + p.C;
@@ -1598,14 +1649,11 @@ int tc_workspace_bytes(const pde_net* net, int order, long long n_points, size_t
   return PDE_OK;
 }
 
-int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
-                          long long n_points, const void* seed, double inv_n, void* sums, void* grad,
-                          void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// Shared launcher: parameter images, the fused kernel in `mode`, fixed-order reduction of the per-CTA partials.
+static int tc_run(const pde_net* net, int order, int mode, const pde_envelope* env, const pde_program* prog, const void* X,
+                  long long n_points, const void* seed, double inv_n, void* J, const void* Jbar, void* sums, void* grad,
+                  void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   using namespace tc;
-  if (!net || !prog) return PDE_ERR_INVALID;
-  const int order = pde_program_order(prog->kind);
-  if (order < 0) return PDE_ERR_INVALID;
-  if (!program_ok(prog)) return PDE_ERR_UNSUPPORTED;
   TcPlan p;
   int rc = make_plan(net, order, n_points, &p);
   if (rc) return rc;
@@ -1627,25 +1675,30 @@ int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde
   pa.n_lin = p.n_lin; pa.D = p.D; pa.H = p.H; pa.params = params; pa.wimg = wimg;
   tc_pack_kernel<<<32, 256, 0, st>>>(pa);
   if (cudaGetLastError() != cudaSuccess) return PDE_ERR_CUDA;
+  count_launch();
 
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.n_h = p.n_h; a.act = net->activation; a.H = p.H;
   a.params = params; a.wimg = wimg;
   a.X = static_cast<const float*>(X); a.n = n_points; a.num_tiles = p.num_tiles;
-  a.prog = prog->kind; a.n_q = pde_program_quantities(prog->kind);
+  a.mode = mode;
+  a.J = static_cast<float*>(J); a.Jbar = static_cast<const float*>(Jbar);
   a.want_grad = (grad != nullptr) || (energy_grad != nullptr);
-  if (env) {
-    a.env.kind = env->kind; a.env.lo = (float)env->lo; a.env.hi = (float)env->hi;
-    for (int i = 0; i < PDE_MAX_DIM; ++i) {
-      a.env.n_nodes[i] = env->n_nodes[i];
-      for (int k = 0; k < PDE_MAX_NODES; ++k) a.env.nodes[i][k] = (float)env->nodes[i][k];
-    }
-  }
-  a.alpha = (float)prog->alpha; a.beta_const = (float)prog->beta_const; a.energy_const = (float)prog->energy_const;
   a.inv_n = (float)inv_n;
-  a.f = static_cast<const float*>(prog->f); a.beta = static_cast<const float*>(prog->beta);
-  a.energy = static_cast<const float*>(prog->energy); a.seed = static_cast<const float*>(seed);
+  if (mode == 0) {
+    a.prog = prog->kind; a.n_q = pde_program_quantities(prog->kind);
+    if (env) {
+      a.env.kind = env->kind; a.env.lo = (float)env->lo; a.env.hi = (float)env->hi;
+      for (int i = 0; i < PDE_MAX_DIM; ++i) {
+        a.env.n_nodes[i] = env->n_nodes[i];
+        for (int k = 0; k < PDE_MAX_NODES; ++k) a.env.nodes[i][k] = (float)env->nodes[i][k];
+      }
+    }
+    a.alpha = (float)prog->alpha; a.beta_const = (float)prog->beta_const; a.energy_const = (float)prog->energy_const;
+    a.f = static_cast<const float*>(prog->f); a.beta = static_cast<const float*>(prog->beta);
+    a.energy = static_cast<const float*>(prog->energy); a.seed = static_cast<const float*>(seed);
+  }
   a.partial = partial; a.psums = psums; a.stash = stash;
   a.PP = p.PP; a.stash_f4 = p.stash_f4;
   a.off_gW0 = p.off_gW0; a.off_gb0 = p.off_gb0; a.off_gW = p.off_gW; a.off_gwL = p.off_gwL; a.off_gbL = p.off_gbL;
@@ -1653,9 +1706,12 @@ int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde
   a.dbg = timeline_buffer();
 #endif
   if (launch_tc(p, a, st) != cudaSuccess) return PDE_ERR_CUDA;
+  count_launch();
+  set_last_path(1);
 #ifdef PDE_TC_TIMELINE
   timeline_dump(a.dbg, st);
 #endif
+  if (mode == 1) return PDE_OK;   // jets out: nothing to reduce
 
   ReduceArgs<float> r;
   memset(&r, 0, sizeof(r));
@@ -1664,10 +1720,48 @@ int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde
   r.off_gW0 = p.off_gW0; r.off_gb0 = p.off_gb0; r.off_gW = p.off_gW; r.off_gwL = p.off_gwL; r.off_gbL = p.off_gbL;
   r.n_params = p.n_params;
   r.grad = static_cast<float*>(grad);
-  r.sums = static_cast<float*>(sums);
-  r.energy_grad = static_cast<float*>(energy_grad);
+  r.sums = (mode == 0) ? static_cast<float*>(sums) : nullptr;
+  r.energy_grad = (mode == 0) ? static_cast<float*>(energy_grad) : nullptr;
   if (launch_reduce<float>(st, r) != cudaSuccess) return PDE_ERR_CUDA;
   return PDE_OK;
 }
+
+int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
+                          long long n_points, const void* seed, double inv_n, void* sums, void* grad,
+                          void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!net || !prog) return PDE_ERR_INVALID;
+  const int order = pde_program_order(prog->kind);
+  if (order < 0) return PDE_ERR_INVALID;
+  if (!program_ok(prog)) return PDE_ERR_UNSUPPORTED;
+  return tc_run(net, order, 0, env, prog, X, n_points, seed, inv_n, nullptr, nullptr, sums, grad, energy_grad, workspace,
+                workspace_bytes, st);
+}
+
+// Network jets on the tensor-core kernel (orders 0 and 1, whose channels are the ABI's): what the WAN losses
+// evaluate for both networks at n_interior points (Poisson_ND.py:105-128, :242-276).
+bool tc_jets_supported(const pde_net* net, int order, long long n_points) {
+  if (order < 0 || order > 1) return false;
+  tc::TcPlan p;
+  return tc::make_plan(net, order, n_points, &p) == PDE_OK;
+}
+
+int tc_jets_forward(const pde_net* net, int order, const void* X, long long n_points, void* J, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+  if (!tc_jets_supported(net, order, n_points)) return PDE_ERR_UNSUPPORTED;
+  if (!J) return PDE_ERR_INVALID;
+  return tc_run(net, order, 1, nullptr, nullptr, X, n_points, nullptr, 1.0, J, nullptr, nullptr, nullptr, nullptr, workspace,
+                workspace_bytes, st);
+}
+
+int tc_jets_backward(const pde_net* net, int order, const void* X, long long n_points, const void* Jbar, void* grad,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!tc_jets_supported(net, order, n_points)) return PDE_ERR_UNSUPPORTED;
+  if (!Jbar || !grad) return PDE_ERR_INVALID;
+  return tc_run(net, order, 2, nullptr, nullptr, X, n_points, nullptr, 1.0, nullptr, Jbar, nullptr, grad, nullptr, workspace,
+                workspace_bytes, st);
+}
+
+void tc_set_path_override(int v) { tc::g_path_override.store(v < -1 || v > 1 ? -1 : v, std::memory_order_relaxed); }
+int tc_get_path_override() { return tc::path_override(); }
 
 }  // namespace pde

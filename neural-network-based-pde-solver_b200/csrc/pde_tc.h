@@ -12,4 +12,13 @@ int tc_workspace_bytes(const pde_net* net, int order, long long n_points, size_t
 int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
                           long long n_points, const void* seed, double inv_n, void* sums, void* grad,
                           void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// network jets (orders 0 / 1) and their reverse sweep on the same kernel
+bool tc_jets_supported(const pde_net* net, int order, long long n_points);
+int tc_jets_forward(const pde_net* net, int order, const void* X, long long n_points, void* J, void* workspace,
+                    size_t workspace_bytes, cudaStream_t stream);
+int tc_jets_backward(const pde_net* net, int order, const void* X, long long n_points, const void* Jbar, void* grad,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// kernel-family override: -1 automatic, 0 generic SIMT kernel, 1 tensor-core kernel wherever its shapes allow
+void tc_set_path_override(int v);
+int tc_get_path_override();
 }  // namespace pde

@@ -135,12 +135,35 @@ _WS = {}
 
 # bench.py sets this to a list to collect (start, stop) CUDA events around each fused-kernel ABI call
 KERNEL_EVENTS = None
-_LAST_PATH = "none"
+_PATH_NAMES = {-1: "none", 0: "simt_fma", 1: "tcgen05"}
 
 
 def last_kernel_path():
-    """Which kernel family served the last fused residual call ("simt_fma" or "tcgen05")."""
-    return _LAST_PATH
+    """Which kernel family the last fused / jets call of this thread actually launched ("simt_fma" or
+    "tcgen05"), as recorded by the library at the launch (pde_last_kernel_path)."""
+    return _PATH_NAMES.get(L.load().pde_last_kernel_path(), "none")
+
+
+def launch_count():
+    """Kernels enqueued by libpde_b200.so in this process so far (pde_launch_count)."""
+    return int(L.load().pde_launch_count())
+
+
+class kernel_path:
+    """Context manager forcing one kernel family: "simt", "tc" or "auto" (pde_set_kernel_path)."""
+    _CODES = {"auto": -1, "simt": 0, "tc": 1}
+
+    def __init__(self, which):
+        self.code = self._CODES[which]
+
+    def __enter__(self):
+        lib = L.load()
+        self.old = lib.pde_kernel_path()
+        L.check(lib.pde_set_kernel_path(self.code), "pde_set_kernel_path")
+        return self
+
+    def __exit__(self, *exc):
+        L.load().pde_set_kernel_path(self.old)
 
 
 class _timed:
@@ -324,12 +347,10 @@ class _Residual(torch.autograd.Function):
         gptr = buf.data_ptr() if fused else None
         eptr = buf.data_ptr() + nparam * buf.element_size() if fused else None
         sptr = buf.data_ptr() + (nparam + 1) * buf.element_size()
-        global _LAST_PATH
         with torch.cuda.device(dev), _timed(dev):
             L.check(lib.pde_residual_loss_grad(C.byref(cnet), C.byref(cenv), C.byref(prog), X.data_ptr(), n, None,
                                                1.0 / n_tot, sptr, gptr, eptr, ws.data_ptr(), ws.numel(), _stream(dev)),
                     "pde_residual_loss_grad")
-        _LAST_PATH = "tcgen05" if lib.pde_query_path(C.byref(cnet), C.byref(prog), n) == 1 else "simt_fma"
         means = combine_forward(buf, nparam, n_tot, group, fused)
         ctx.fused = fused
         ctx.has_energy = energy is not None

@@ -20,13 +20,9 @@ TOL = 1e-5
 
 @pytest.fixture(autouse=True)
 def _force_tc():
-    old = os.environ.get("PDE_B200_PATH")
-    os.environ["PDE_B200_PATH"] = "tc"
-    yield
-    if old is None:
-        os.environ.pop("PDE_B200_PATH", None)
-    else:
-        os.environ["PDE_B200_PATH"] = old
+    import pde_b200 as pb
+    with pb.ops.kernel_path("tc"):
+        yield
 
 
 def _seq(Ws, bs, act, dtype=torch.float32):
@@ -155,9 +151,9 @@ def test_tc_large_batch_against_fp64_generic_kernel():
     l32 = residual_means(n32, X32, ProgramSpec(L.PROG_PINN, -1.0), espec, f=f32)[0]
     assert pb.ops.last_kernel_path() == "tcgen05"
     l32.backward()
-    os.environ["PDE_B200_PATH"] = "simt"
-    l64 = residual_means(n64, X32.double(), ProgramSpec(L.PROG_PINN, -1.0), espec, f=f32.double())[0]
-    l64.backward()
+    with pb.ops.kernel_path("simt"):
+        l64 = residual_means(n64, X32.double(), ProgramSpec(L.PROG_PINN, -1.0), espec, f=f32.double())[0]
+        l64.backward()
     assert abs(l32.item() - l64.item()) <= TOL * abs(l64.item())
     assert_grads_close(_grads(lin32), _grads(lin64), TOL, "2^20 points")
 
@@ -192,9 +188,13 @@ def test_tc_chunk_linearity_full_size_and_determinism():
 
 def test_path_selection():
     """Default routing: tensor-core kernel for the shapes it covers above 4096 points, generic kernel
-    otherwise (fp64, wide nets, 7 jet channels); PDE_B200_PATH overrides."""
+    otherwise (fp64, wide nets, 7 jet channels); pde_set_kernel_path overrides."""
     import pde_b200 as pb
-    os.environ.pop("PDE_B200_PATH", None)
+    with pb.ops.kernel_path("auto"):
+        _path_selection(pb)
+
+
+def _path_selection(pb):
     X = torch.rand(8192, 3, device="cuda") * 2
     f = torch.ones(8192, 1, device="cuda")
     m = pb.poisson.SolutionNet(3, 64, 5, "FBC").cuda()
@@ -218,3 +218,129 @@ def test_path_selection():
     m128 = pb.poisson.SolutionNet(3, 128, 5, "FBC").cuda()
     pb.poisson.pinn_residual_loss(m128, X, f, 2.0)
     assert pb.ops.last_kernel_path() == "simt_fma"
+    # network jets of order <= 1 (what the WAN losses evaluate for both networks) ride the tensor-core kernel too
+    J = pb.mlp_jets(m, X, 1)
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    J.sum().backward()
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    pb.mlp_jets(m, X, 2)
+    assert pb.ops.last_kernel_path() == "simt_fma"         # Hessian-diagonal channels: generic kernel
+    v = pb.poisson.CriticNet(3, 64, 3).cuda()
+    Xr = X.clone().requires_grad_(True)
+    lu, lv, _, _ = pb.poisson.wan_losses(m, v, Xr, f, 2.0)
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    lv.backward()
+    assert pb.ops.last_kernel_path() == "tcgen05"
+
+
+@pytest.mark.parametrize("d,w,depth,order,act,N", [(3, 64, 5, 1, "sin", 777), (2, 50, 4, 1, "tanh", 4099), (1, 20, 3, 1, "tanh", 100),
+                                                 (5, 24, 3, 1, "sin", 64), (2, 64, 4, 0, "sin", 1000), (4, 9, 3, 1, "sin", 333)])
+def test_tc_jets_forward_backward_vs_numpy_oracle(d, w, depth, order, act, N):
+    """pde_jets_forward / pde_jets_backward on the tensor-core kernel (orders 0, 1): jets and the reverse sweep with
+    arbitrary cotangents vs oracle/jets_numpy (the same check test_gpu_poisson runs on the generic kernel)."""
+    import pde_b200 as pb
+    from oracle import jets_numpy as O
+    rng = np.random.default_rng(50 + d)
+    Ws, bs = _rand_net(rng, d, w, depth)
+    X = rng.uniform(0, 2, (N, d)).astype(np.float32).astype(np.float64)
+    Jbar = rng.normal(size=(N, 1 + order * d)).astype(np.float32).astype(np.float64)
+    A = O.SIN if act == "sin" else O.TANH
+    J, cache = O.mlp_jets_forward(Ws, bs, X, A, order)
+    gWs, gbs = O.mlp_jets_backward(Ws, bs, cache, Jbar)
+    net, lin = _seq(Ws, bs, act)
+    Jg = pb.mlp_jets(net, torch.tensor(X, dtype=torch.float32, device="cuda"), order)
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    assert np.max(np.abs(Jg.detach().double().cpu().numpy() - J)) <= 5 * TOL * max(1.0, np.abs(J).max())
+    Jg.backward(torch.tensor(Jbar, dtype=torch.float32, device="cuda"))
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    assert_grads_close(_grads(lin), (gWs, gbs), TOL, f"jets d{d} w{w} {act} order{order}")
+
+
+def test_tc_poisson_wan_vs_reference_golden_and_large_batch():
+    """wan_losses with both networks' jets and reverse sweeps on the tensor-core kernel: (i) the reference golden
+    (d = 2, forced onto the tensor-core path), (ii) 2^16 points vs the float64 generic kernels."""
+    import pde_b200 as pb
+    from conftest import assert_grads_golden, assert_loss_close
+    g = load_golden("poisson_wan_d2_w16")
+    dtype = torch.float32
+
+    def build(prefix, cls, *args):
+        Ws, bs = net_from(g, prefix)
+        m = cls(Ws[0].shape[1], Ws[0].shape[0], len(Ws), *args).double()
+        lin = [x for x in m.net if isinstance(x, torch.nn.Linear)]
+        with torch.no_grad():
+            for l, W, b in zip(lin, Ws, bs):
+                l.weight.copy_(torch.tensor(W)); l.bias.copy_(torch.tensor(b))
+        return m.to("cuda", dtype), lin
+    um, ul = build("u_", pb.poisson.SolutionNet, "FBC")
+    vm, vl = build("v_", pb.poisson.CriticNet)
+    X = torch.tensor(g["X"], dtype=dtype, device="cuda", requires_grad=True)
+    f = torch.tensor(g["f"], dtype=dtype, device="cuda")
+    lu, lv, weak, pn = pb.poisson.wan_losses(um, vm, X, f, float(g["L"]), v_reg_weight=float(g["v_reg_weight"]))
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    for got, key in ((lu, "loss_u"), (lv, "loss_v"), (weak, "weak"), (pn, "phi_norm")):
+        assert_loss_close(got, g, key, dtype, "tc wan")
+    lu.backward(retain_graph=True)
+    assert_grads_golden(_grads(ul), g, "lu_u_", dtype)
+    assert_grads_golden(_grads(vl), g, "lu_v_", dtype)
+    um.zero_grad(); vm.zero_grad()
+    lv.backward()
+    assert_grads_golden(_grads(ul), g, "lv_u_", dtype)
+    assert_grads_golden(_grads(vl), g, "lv_v_", dtype)
+
+    # (ii) n_interior = 2^16, 3-D, default-width networks: float32 tensor-core path vs float64 generic path
+    import copy
+    torch.manual_seed(4)
+    u32 = pb.poisson.SolutionNet(3, 64, 5, "FBC").cuda(); v32 = pb.poisson.CriticNet(3, 64, 3).cuda()
+    u64, v64 = copy.deepcopy(u32).double(), copy.deepcopy(v32).double()
+    N = 1 << 16
+    X = (torch.rand(N, 3, device="cuda") * 1.9 + 0.05).requires_grad_(True)
+    f = pb.poisson.rhs_f_for_u_sin(X.detach(), 2.0, [1, 1, 1])
+    res = {}
+    for tag, (um, vm, Xc, fc, path) in {"tc": (u32, v32, X, f, "tc"),
+                                        "ref": (u64, v64, X.detach().double().requires_grad_(True), f.double(), "simt")}.items():
+        with pb.ops.kernel_path(path):
+            lu, lv, weak, pn = pb.poisson.wan_losses(um, vm, Xc, fc, 2.0, v_reg_weight=0.5)
+            lu.backward(retain_graph=True)
+            gu = [p.grad.double().clone() for p in um.parameters()]
+            um.zero_grad(); vm.zero_grad()
+            lv.backward()
+            gv = [p.grad.double().clone() for p in vm.parameters()]
+        res[tag] = (lu.item(), lv.item(), gu, gv)
+    assert abs(res["tc"][0] - res["ref"][0]) <= TOL * abs(res["ref"][0])
+    assert abs(res["tc"][1] - res["ref"][1]) <= TOL * abs(res["ref"][1])
+    for k in (2, 3):
+        scale = max(float(t.abs().max()) for t in res["ref"][k])
+        for a, b in zip(res["tc"][k], res["ref"][k]):
+            assert float((a - b).abs().max()) <= TOL * scale
+
+
+def test_tc_adjoint_scale_follows_the_residual():
+    """The fp16 operand split of the reverse sweep works on adjoints scaled by a power of two that is re-derived per
+    tile: a batch whose residual grows by 1e7 along a CTA's tile range (source term O(1) on the first tiles, O(1e7)
+    later, and the other way round) must give the same loss and gradient as the float64 generic kernel."""
+    import pde_b200 as pb
+    from pde_b200 import _lib as L
+    from pde_b200.ops import EnvelopeSpec, ProgramSpec, residual_means
+    rng = np.random.default_rng(9)
+    Ws, bs = _rand_net(rng, 3, 64, 5)
+    n32, lin32 = _seq(Ws, bs, "sin")
+    n64, lin64 = _seq(Ws, bs, "sin", torch.float64)
+    N = 148 * 64 * 6                      # six tiles per CTA
+    X = torch.rand(N, 3, device="cuda") * 1.9 + 0.05
+    espec = EnvelopeSpec(L.ENV_POLY, 0.0, 2.0)
+    tile = torch.arange(N, device="cuda") // 64
+    for ramp in (1, -1):
+        pos = (tile % 6).float() if ramp > 0 else (5 - tile % 6).float()
+        f = torch.randn(N, device="cuda") * torch.pow(10.0, pos * 1.4)     # 1 ... 1e7 within every CTA's range
+        for net in (n32, n64):
+            net.zero_grad()
+        l32 = residual_means(n32, X, ProgramSpec(L.PROG_PINN, -1.0), espec, f=f)[0]
+        assert pb.ops.last_kernel_path() == "tcgen05"
+        l32.backward()
+        with pb.ops.kernel_path("simt"):
+            l64 = residual_means(n64, X.double(), ProgramSpec(L.PROG_PINN, -1.0), espec, f=f.double())[0]
+            l64.backward()
+        assert math.isfinite(l32.item())
+        assert abs(l32.item() - l64.item()) <= TOL * abs(l64.item())
+        assert_grads_close(_grads(lin32), _grads(lin64), TOL, f"ramp {ramp}")

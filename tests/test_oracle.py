@@ -481,7 +481,7 @@ def test_reference_spread_is_recorded_for_every_fixture():
     for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         with np.load(f) as z:
             c = [k for k in z.files if k.startswith("c64_")]
-            assert c and any(k.startswith("ref32_") for k in z.files), f
+            assert c and any(k.startswith("ref32_") for k in z.files) and any(k.startswith("e32_") for k in z.files), f
             for k in c:
                 ref = np.max(np.abs(z[k[4:]]))
                 if np.isfinite(z[k][0]) and ref > 0 and not k[4:].startswith(("u", "grad_u", "lap_u")):

@@ -1,5 +1,5 @@
 """Development check (GPU): tcgen05 path vs the numpy oracle, per-tensor errors printed.
-    PDE_B200_PATH is set per case; run as `python tools/tc_check.py [quick]`."""
+    the kernel family is set per case (pde_set_kernel_path); run as `python tools/tc_check.py [quick]`."""
 import math
 import os
 import sys
@@ -52,7 +52,7 @@ def report(tag, loss, want, lin, gWs, gbs):
 
 
 def case(d, w, depth, act, prog, env_kind, N, seed=0, path="tc"):
-    os.environ["PDE_B200_PATH"] = path
+    L.load().pde_set_kernel_path({"simt": 0, "tc": 1}[path])
     rng = np.random.default_rng(seed)
     net, lin, Ws, bs = make_net(d, w, depth, act, rng)
     X = rng.uniform(0.05, 1.95, (N, d)).astype(np.float32).astype(np.float64)
@@ -96,10 +96,10 @@ def big_case(N=1 << 20, d=3, seed=3):
     X32 = X.float(); f32 = f.float()
     X = X32.double(); f = f32.double()
     espec = EnvelopeSpec(L.ENV_POLY, 0.0, 2.0)
-    os.environ["PDE_B200_PATH"] = "tc"
+    L.load().pde_set_kernel_path(1)
     l32 = residual_means(net32, X32, ProgramSpec(L.PROG_PINN, -1.0), espec, f=f32)[0]
     l32.backward()
-    os.environ["PDE_B200_PATH"] = "simt"
+    L.load().pde_set_kernel_path(0)
     l64 = residual_means(net64, X, ProgramSpec(L.PROG_PINN, -1.0), espec, f=f)[0]
     l64.backward()
     torch.cuda.synchronize()
