@@ -238,11 +238,19 @@ typedef struct pde_peers {
  * no fence, no separate signal); the rank then polls its own slots and adds the values in rank order
  * (bit-identical result on every rank, independent of arrival order).  One launch; `seq` (device uint32,
  * zero at start) counts the calls so the kernel can be replayed from a CUDA graph.  A peer that does not
- * arrive within ~2 s poisons the result with NaN instead of hanging the GPU.
+ * arrive within the exchange timeout (below) poisons the result with NaN instead of hanging the GPU.
  * Replaces: the gradient exchange a data-parallel run of train_poisson_nd needs after loss.backward()
  * (Poisson_ND.py:240; the reference itself is single-device), SURVEY.md §8e. */
 int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int64_t n, int64_t slot_elems,
                           void* seq, void* stream);
+
+/* Failure reporting of the exchange.  Every rank must make the same sequence of pde_allreduce_oneshot calls
+ * (lockstep, as for any collective).  A rank waits for its peers for at most the exchange timeout — process wide,
+ * default 600 s, 0 = for ever — and on expiry poisons ITS OWN result with NaN and counts the event in its control
+ * block; peers that did receive this rank's words are not affected and cannot know, so the host must look:
+ * pde_exchange_errors synchronises `stream` and returns the number of timed-out elements seen so far on this rank. */
+int pde_set_exchange_timeout(double seconds);
+int pde_exchange_errors(const pde_peers* peers, uint32_t* timeouts, void* stream);
 
 #ifdef __cplusplus
 }

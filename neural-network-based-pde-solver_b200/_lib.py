@@ -20,7 +20,7 @@ EXPORTS = [
     "pde_residual_loss_grad", "pde_wan_pointwise", "pde_query_path", "pde_sample_points_rhs", "pde_adam_step",
     "pde_keep_best", "pde_peer_bytes", "pde_peer_alloc", "pde_peer_open", "pde_peer_close", "pde_peer_free",
     "pde_allreduce_oneshot", "pde_query_jets_path", "pde_set_kernel_path", "pde_kernel_path", "pde_last_kernel_path",
-    "pde_launch_count",
+    "pde_launch_count", "pde_set_exchange_timeout", "pde_exchange_errors",
 ]
 MAX_PEERS = 8
 
@@ -105,6 +105,8 @@ def load():
     lib.pde_peer_close.argtypes = [vp]
     lib.pde_peer_free.argtypes = [vp]
     lib.pde_allreduce_oneshot.argtypes = [C.POINTER(Peers), i32, vp, i64, i64, vp, vp]
+    lib.pde_set_exchange_timeout.argtypes = [dbl]
+    lib.pde_exchange_errors.argtypes = [C.POINTER(Peers), C.POINTER(C.c_uint32), vp]
     lib.pde_query_jets_path.argtypes = [C.POINTER(Net), i32, i64]
     lib.pde_set_kernel_path.argtypes = [i32]
     for name in EXPORTS:

@@ -7,6 +7,11 @@ Set-up (once): every rank allocates a peer-visible buffer through the library, t
 handles travel through ``torch.distributed.all_gather_object`` and every rank maps its peers' buffers.
 The data path never touches NCCL; ``torch.distributed`` is plumbing for the handle exchange only.
 Single node only (the ranks of one NVSwitch box), world <= 8.
+
+Lockstep: every rank must issue the same sequence of ``all_reduce_`` calls.  A rank waits for its peers for at most
+``timeout_s`` (default 600 s, ``PDE_B200_EXCHANGE_TIMEOUT_S`` overrides, 0 = for ever); if that expires its result is
+NaN and an error word is set on the device, which ``check()`` turns into an exception — call it wherever the host
+synchronises anyway (FusedTrainer and bench.py do).
 """
 from __future__ import annotations
 
@@ -20,7 +25,7 @@ from .ops import _stream
 
 
 class NvlinkAllReduce:
-    def __init__(self, group=None, max_elems=1 << 16, dtype=torch.float32, device=None):
+    def __init__(self, group=None, max_elems=1 << 16, dtype=torch.float32, device=None, timeout_s=None):
         lib = L.load()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -51,6 +56,9 @@ class NvlinkAllReduce:
                     self.peers.base[r] = p.value
                     self._opened.append(p.value)
         self.seq = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        import os
+        timeout_s = float(os.environ.get("PDE_B200_EXCHANGE_TIMEOUT_S", "600") if timeout_s is None else timeout_s)
+        L.check(lib.pde_set_exchange_timeout(timeout_s), "pde_set_exchange_timeout")
         dist.barrier(group=group)      # every rank has mapped every buffer before the first call
 
     def all_reduce_(self, t: torch.Tensor):
@@ -60,6 +68,16 @@ class NvlinkAllReduce:
             L.check(L.load().pde_allreduce_oneshot(C.byref(self.peers), self.dt, t.data_ptr(), t.numel(), self.slot,
                                                    self.seq.data_ptr(), _stream(self.dev)), "pde_allreduce_oneshot")
         return t
+
+    def check(self):
+        """Synchronise the current stream and raise if any exchange of this rank ever timed out (its result was
+        poisoned with NaN; the peers' replicas have diverged from this one)."""
+        n = C.c_uint32(0)
+        with torch.cuda.device(self.dev):
+            L.check(L.load().pde_exchange_errors(C.byref(self.peers), C.byref(n), _stream(self.dev)), "pde_exchange_errors")
+        if n.value:
+            raise L.PdeError(f"NVLink exchange: rank {self.rank} gave up waiting for a peer on {n.value} element(s); "
+                             "its gradients were poisoned with NaN and the replicas have diverged")
 
     def close(self):
         """Unmap the peers' buffers and free the own one (after a barrier: nobody may still read it)."""

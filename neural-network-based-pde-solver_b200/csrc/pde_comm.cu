@@ -19,11 +19,21 @@
 // The call counter lives in device memory, so the kernel is CUDA-graph replayable; elements are
 // independent, so any number of blocks can run (the last one to finish advances the counter).
 //
+// Lockstep requirement and failure reporting.  Like any collective, every rank must make the same sequence of
+// calls.  A rank waits for its peers' words for at most the exchange timeout (pde_set_exchange_timeout, default
+// 600 s, 0 = wait for ever; host-side skew such as a checkpoint on one rank or a first-call module load is
+// therefore harmless).  If the wait does expire the rank poisons ITS result with NaN and increments an error
+// word in its own control block; the peers, which did receive this rank's words, cannot know, so the host side
+// must look: pde_exchange_errors() reads the word (comm.NvlinkAllReduce.check() raises on it, and the fused
+// trainer / bench.py call that at every point where they synchronise anyway).
+//
 // Peer buffers are plain cudaMalloc allocations shared with CUDA IPC handles (pde_peer_alloc /
 // pde_peer_open); the handles travel through torch.distributed's object collectives once at set-up.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "../../include/pde_b200.h"
 
@@ -31,7 +41,9 @@ namespace pde { void count_launch(int k); }   // pde_abi.cu: launch counter behi
 
 namespace {
 
-constexpr int CTRL_BYTES = 512;     // local control words (block-completion counter) in front of the slots
+constexpr int CTRL_BYTES = 512;     // local control words in front of the slots: [0] block-completion counter, [16] timeouts
+constexpr int CTRL_ERR_WORD = 16;   // uint32 index of the error counter inside the control block
+std::atomic<long long> g_spin_limit{600ll * 2000000000ll};   // clock64 ticks; <= 0: no timeout
 constexpr int COMM_THREADS = 256, COMM_MAX_BLOCKS = 16;
 
 // (value, flag) travels as ONE 64-bit scalar access: single-copy atomic in the PTX memory model
@@ -107,7 +119,7 @@ __global__ void __launch_bounds__(COMM_THREADS) allreduce_oneshot_kernel(const C
           }
         }
       }
-      if (pending && clock64() - t0 > a.spin_limit) { bad = true; break; }
+      if (pending && a.spin_limit > 0 && clock64() - t0 > a.spin_limit) { bad = true; break; }
     }
     // rank-ordered sum 0, 1, ..., W-1 on every rank
     T acc = T(0);
@@ -123,7 +135,10 @@ __global__ void __launch_bounds__(COMM_THREADS) allreduce_oneshot_kernel(const C
         acc = (p == 0) ? v : acc + v;
       }
     }
-    if (bad) acc = (T)__longlong_as_double(0x7ff8000000000000ll);
+    if (bad) {
+      acc = (T)__longlong_as_double(0x7ff8000000000000ll);
+      atomicAdd(reinterpret_cast<uint32_t*>(a.base[a.rank]) + CTRL_ERR_WORD, 1u);   // seen by pde_exchange_errors()
+    }
     static_cast<T*>(a.buf)[i] = acc;
   }
   // the last block to finish advances the call counter: by then every block has read it
@@ -200,7 +215,7 @@ int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int6
   const int wpe = dtype == PDE_F64 ? 2 : 1;
   a.n_words = n * wpe; a.slot_words = slot_elems * wpe; a.is_f64 = dtype == PDE_F64;
   a.buf = buf; a.seq = static_cast<uint32_t*>(seq);
-  a.spin_limit = 4000000000ll;   // ~2 s at 1.9 GHz
+  a.spin_limit = g_spin_limit.load(std::memory_order_relaxed);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long g = (n + COMM_THREADS - 1) / COMM_THREADS;
   const int grid = (int)(g < 1 ? 1 : (g > COMM_MAX_BLOCKS ? COMM_MAX_BLOCKS : g));
@@ -208,6 +223,21 @@ int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int6
   else allreduce_oneshot_kernel<double><<<grid, COMM_THREADS, 0, st>>>(a);
   pde::count_launch(1);
   return cudaGetLastError() == cudaSuccess ? PDE_OK : PDE_ERR_CUDA;
+}
+
+int pde_set_exchange_timeout(double seconds) {
+  if (!(seconds >= 0.0) || seconds > 1.0e6) return PDE_ERR_INVALID;
+  g_spin_limit.store((long long)(seconds * 2.0e9), std::memory_order_relaxed);   // clock64 ticks at <= 2 GHz; 0 = no timeout
+  return PDE_OK;
+}
+
+int pde_exchange_errors(const pde_peers* peers, uint32_t* timeouts, void* stream) {
+  if (!peers || !timeouts || peers->rank < 0 || peers->rank >= PDE_MAX_PEERS || !peers->base[peers->rank]) return PDE_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t* word = static_cast<const uint32_t*>(peers->base[peers->rank]) + CTRL_ERR_WORD;
+  if (cudaMemcpyAsync(timeouts, word, sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) { cudaGetLastError(); return PDE_ERR_CUDA; }
+  if (cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return PDE_ERR_CUDA; }
+  return PDE_OK;
 }
 
 }  // extern "C"

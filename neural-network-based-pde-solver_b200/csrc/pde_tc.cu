@@ -331,25 +331,71 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
   asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
-// stash store policy (development switch): 0 = st.global.cg (L2 only), 1 = default st.global (write-through L1), 2 = st.global.cs
-#ifndef PDE_TC_STASH_ST
-#define PDE_TC_STASH_ST 0
+// The stash is rewritten every tile and dead after the tile's reverse sweep, but an L2 line that is merely dirty is
+// still written back to HBM when it is evicted.  PDE_TC_STASH_POLICY: 0 = plain st.global.cg / ld.global.cg;
+// 1 = stash traffic carries an L2 evict_last policy and the streamed inputs (X, f, beta) evict_first, so that the
+// one-pass inputs do not push stash lines out; 2 = 1 + every stash line is discarded (discard.global.L2: dropped
+// without write-back) once the reverse sweep has consumed it; 3 = discard only.
+#ifndef PDE_TC_STASH_POLICY
+#define PDE_TC_STASH_POLICY 1
 #endif
-__device__ __forceinline__ void stash_store(float4* p, float4 v) {
-#if PDE_TC_STASH_ST == 1
-  *p = v;
-#elif PDE_TC_STASH_ST == 2
-  __stcs(p, v);
-#elif PDE_TC_STASH_ST == 3   // timing experiment only: no store (wrong results)
-  (void)p; (void)v;
-#else
-  __stcg(p, v);
-#endif
+constexpr bool STASH_HINT = (PDE_TC_STASH_POLICY == 1 || PDE_TC_STASH_POLICY == 2);
+constexpr bool STASH_DISCARD = (PDE_TC_STASH_POLICY >= 2);
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void stash_store(float4* p, float4 v, uint64_t pol) {
+  if constexpr (STASH_HINT)
+    asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+  else
+    __stcg(p, v);
+}
+__device__ __forceinline__ void stash_store(float2* p, float2 v, uint64_t pol) {
+  if constexpr (STASH_HINT)
+    asm volatile("st.global.cg.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+  else
+    __stcg(p, v);
+}
+__device__ __forceinline__ float4 stash_load(const float4* p, uint64_t pol) {
+  if constexpr (STASH_HINT) {
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+  } else {
+    return __ldcg(p);
+  }
+}
+__device__ __forceinline__ float2 stash_load(const float2* p, uint64_t pol) {
+  if constexpr (STASH_HINT) {
+    float2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+  } else {
+    return __ldcg(p);
+  }
+}
+// one-pass inputs
+__device__ __forceinline__ float stream_load(const float* p, uint64_t pol) {
+  if constexpr (STASH_HINT) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+  } else {
+    return *p;
+  }
+}
+// 128-byte line at p (128-byte aligned) will not be read again before it is rewritten: drop it from L2
+__device__ __forceinline__ void stash_discard(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 __device__ __forceinline__ void stsm_x2(uint32_t addr, uint32_t r0, uint32_t r1) {
   asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1,%2};" ::"r"(addr), "r"(r0), "r"(r1) : "memory");
 }
-__device__ __forceinline__ void stash_store(float2* p, float2 v) { __stcg(p, v); }
 // stashed vector <-> the thread's element array
 __device__ __forceinline__ void to_arr(const float4& sv, float (&v)[4]) { v[0] = sv.x; v[1] = sv.y; v[2] = sv.z; v[3] = sv.w; }
 __device__ __forceinline__ void to_arr(const float2& sv, float (&v)[2]) { v[0] = sv.x; v[1] = sv.y; }
@@ -674,6 +720,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         v[1] = rh ? t[3] : t[1];
       }
     };
+    uint64_t pol_stash = 0, pol_stream = 0;
+    if constexpr (STASH_HINT) {
+      pol_stash = l2_policy_evict_last();
+      pol_stream = l2_policy_evict_first();
+    }
     uint32_t ph_d = 0, ph_w = 0;
     int reg = 0;   // region the next D-consuming step reads
     bool w_pending = false;   // a bar_w commit has been issued that nobody waited for yet
@@ -788,7 +839,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       for (int k = 0; k < XR; ++k) {
         const int i = tid + k * NEPI * 32;
         const long long gp = (long long)tile * TP + i / D;
-        xnext[k] = (i < TP * D && gp < a.n) ? a.X[gp * D + (i % D)] : 0.f;
+        xnext[k] = (i < TP * D && gp < a.n) ? stream_load(a.X + gp * D + (i % D), pol_stream) : 0.f;
       }
     };
     if (tile_begin < tile_end) load_x(tile_begin);
@@ -813,8 +864,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       if (tile + 1 < tile_end) load_x(tile + 1);
       float fv = 0.f, bt = a.beta_const;
       if (tid < TP && base + tid < a.n) {
-        if (a.f) fv = a.f[base + tid];
-        if (a.beta) bt = a.beta[base + tid];
+        if (a.f) fv = stream_load(a.f + base + tid, pol_stream);
+        if (a.beta) bt = stream_load(a.beta + base + tid, pol_stream);
       }
       if (do_bwd) {
         for (int i = tid; i < D * 32; i += NEPI * 32) {
@@ -896,7 +947,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           if (do_bwd) {
             if constexpr (!L0) {
 #pragma unroll
-              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), from_arr(z[c]));
+              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), from_arr(z[c]), pol_stash);
             }
           }
 #endif
@@ -908,8 +959,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           act_eval<NE>(act, z[0], big, sv0, sv1);
 #if PDE_TC_STASH_EARLY
           if (do_bwd) {
-            stash_store(stash_at(l, j, 0), from_arr(sv0));
-            stash_store(stash_at(l, j, 1), from_arr(sv1));
+            stash_store(stash_at(l, j, 0), from_arr(sv0), pol_stash);
+            stash_store(stash_at(l, j, 1), from_arr(sv1), pol_stash);
           }
 #endif
           if constexpr (PDE_TC_F32X2 && NE % 2 == 0 && ND >= 1) {
@@ -964,11 +1015,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
 #if !PDE_TC_STASH_EARLY
           if (do_bwd) {
-            stash_store(stash_at(l, j, 0), from_arr(sv0));
-            stash_store(stash_at(l, j, 1), from_arr(sv1));
+            stash_store(stash_at(l, j, 0), from_arr(sv0), pol_stash);
+            stash_store(stash_at(l, j, 1), from_arr(sv1), pol_stash);
             if constexpr (!L0) {
 #pragma unroll
-              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), from_arr(z[c]));
+              for (int c = 1; c < C; ++c) stash_store(stash_at(l, j, 1 + c), from_arr(z[c]), pol_stash);
             }
           }
 #endif
@@ -1091,20 +1142,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         // are fetched as soon as chunk j has consumed them (no rotation copies).
         StashV cur[NV], prv[NV];
         auto load_cur = [&](int j) {
-          cur[0] = __ldcg(stash_at(l, j, 0)); cur[1] = __ldcg(stash_at(l, j, 1));
+          cur[0] = stash_load(stash_at(l, j, 0), pol_stash); cur[1] = stash_load(stash_at(l, j, 1), pol_stash);
           if constexpr (LK >= 1) {
 #pragma unroll
-            for (int v = 2; v < NV; ++v) cur[v] = __ldcg(stash_at(l, j, v));
+            for (int v = 2; v < NV; ++v) cur[v] = stash_load(stash_at(l, j, v), pol_stash);
           }
         };
         // at the top layer A_{n_h-2} is still in T1 from the forward sweep: nothing to rebuild
         constexpr bool REFILL = (LK >= 1) && !TOP;
         auto load_prv = [&](int j) {
           if constexpr (REFILL) {
-            prv[0] = __ldcg(stash_at(l - 1, j, 0)); prv[1] = __ldcg(stash_at(l - 1, j, 1));
+            prv[0] = stash_load(stash_at(l - 1, j, 0), pol_stash); prv[1] = stash_load(stash_at(l - 1, j, 1), pol_stash);
             if constexpr (LK >= 2) {
 #pragma unroll
-              for (int v = 2; v < NV; ++v) prv[v] = __ldcg(stash_at(l - 1, j, v));
+              for (int v = 2; v < NV; ++v) prv[v] = stash_load(stash_at(l - 1, j, v), pol_stash);
             }
           }
         };
@@ -1255,6 +1306,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), abr[c]);
             }
             load_cur(j + 1);
+          }
+          if constexpr (STASH_DISCARD) {
+            // layer l's stash lines of chunk j have been consumed (as `cur` here, as `prv` one layer up)
+            if ((lane & 7) == 0) {
+#pragma unroll
+              for (int v = 0; v < ((LK >= 1) ? NV : 2); ++v) stash_discard(stash_at(l, j, v));
+            }
           }
           uint32_t zk[C][NE];
           pack_chunk(zb, zk);
@@ -1504,6 +1562,10 @@ static cudaError_t launch_one(const TcPlan& p, const TcArgs& a, cudaStream_t st)
 
 template <int ACT>
 static cudaError_t launch_act(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
+#ifdef PDE_TC_ONLY_CFG2   // development builds (A/B timing of kernel variants): the headline instantiation only
+  if (p.D == 3 && p.order == 2 && ACT == 0) return launch_one<3, 2, 0>(p, a, st);
+  return cudaErrorInvalidValue;
+#else
   switch (p.D * 3 + p.order) {
     case 3: return launch_one<1, 0, ACT>(p, a, st);
     case 4: return launch_one<1, 1, ACT>(p, a, st);
@@ -1521,6 +1583,7 @@ static cudaError_t launch_act(const TcPlan& p, const TcArgs& a, cudaStream_t st)
     case 16: return launch_one<5, 1, ACT>(p, a, st);
     default: return cudaErrorInvalidValue;
   }
+#endif
 }
 
 static cudaError_t launch_tc(const TcPlan& p, const TcArgs& a, cudaStream_t st) {

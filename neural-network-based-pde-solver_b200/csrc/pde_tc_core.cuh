@@ -164,17 +164,21 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 }
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
 #if PDE_TC_FP16
+  // hi = rn16(x);  lo = rn16(x - hi).  The residual comes from the mixed-precision FMA of sm_100
+  // (fma.rn.f32.f16: half x half + float, SASS FHFMA, which selects the half of the packed register itself):
+  // x - hi = hi * (-1) + x, exact, one instruction per element instead of an unpack-convert and a subtract.
   hi = pack_f16x2(a, b);
-  float ha, hb;
+  float ra, rb;
   asm("{\n\t"
-      ".reg .b16 l, h;\n\t"
+      ".reg .b16 l, h, m;\n\t"
       "mov.b32 {l, h}, %2;\n\t"
-      "cvt.f32.f16 %0, l;\n\t"
-      "cvt.f32.f16 %1, h;\n\t"
+      "mov.b16 m, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %0, l, m, %3;\n\t"
+      "fma.rn.f32.f16 %1, h, m, %4;\n\t"
       "}"
-      : "=f"(ha), "=f"(hb)
-      : "r"(hi));
-  lo = pack_f16x2(a - ha, b - hb);
+      : "=f"(ra), "=f"(rb)
+      : "r"(hi), "f"(a), "f"(b));
+  lo = pack_f16x2(ra, rb);
 #else
   hi = pack_bf16x2(a, b);
   float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
