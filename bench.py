@@ -574,7 +574,7 @@ def main():
                     "how": "pinned host X,f -> device on a copy stream one step ahead; loss .item()-style readback every step"},
             "gpu_launches": launches,
             "gpu_launches_how": ("pde_launch_count() delta over the timed region (counted at the library's launch sites): per step "
-                                 "tc_pack_kernel, tc_kernel<3,2,sin>, reduce_kernel" + (", allreduce_oneshot_kernel" if world > 1 else "")
+                                 "tc_pack_kernel, tc_kernel<3,2,sin>, reduce_kernel" + (" (with the NVLink exchange in its tail)" if world > 1 else "")
                                  + "; the autograd bridge's own ATen kernels (zero-fill, scale by dLoss, view into p.grad) are not counted"),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": prof.get("dram_bytes_per_launch"),

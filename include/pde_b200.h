@@ -244,6 +244,17 @@ typedef struct pde_peers {
 int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int64_t n, int64_t slot_elems,
                           void* seq, void* stream);
 
+/* The fused loss step with the exchange folded into its reduction: the kernel that sums the per-CTA
+ * partial gradients pushes every reduced element to the peers, collects theirs and writes the rank-ordered sum, so a
+ * data-parallel step is pack + fused kernel + reduce-and-exchange — no separate all-reduce launch.
+ *   result : device, [grad (n_params) | dE (1) | sums (K)] contiguous, every element summed over the ranks
+ *   peers, slot_elems (>= n_params + 1 + K), seq : as for pde_allreduce_oneshot (same buffers, same call counter).
+ * Replaces: loss.backward() + the gradient exchange of a data-parallel train_poisson_nd step (Poisson_ND.py:240). */
+int pde_residual_loss_grad_exchange(const pde_net* net, const pde_envelope* env, const pde_program* prog,
+                                    const void* X, int64_t n_points, const void* seed, double inv_n, void* result,
+                                    void* workspace, size_t workspace_bytes, const pde_peers* peers,
+                                    int64_t slot_elems, void* seq, void* stream);
+
 /* Failure reporting of the exchange.  Every rank must make the same sequence of pde_allreduce_oneshot calls
  * (lockstep, as for any collective).  A rank waits for its peers for at most the exchange timeout — process wide,
  * default 600 s, 0 = for ever — and on expiry poisons ITS OWN result with NaN and counts the event in its control

@@ -194,7 +194,7 @@ int validate_env(const pde_envelope* env) {
 template <typename T>
 int run_net(const pde_net* net, int order, int mode, const pde_envelope* env, const pde_program* prog,
             const void* X, long long n, const void* seed, double inv_n, void* J, const void* Jbar, void* sums,
-            void* grad, void* energy_grad, void* ws, size_t ws_bytes, cudaStream_t st) {
+            void* grad, void* energy_grad, void* ws, size_t ws_bytes, cudaStream_t st, const ExchangeReq* ex = nullptr) {
   Plan p;
   int rc = make_plan<T>(net, order, n, &p);
   if (rc) return rc;
@@ -248,6 +248,12 @@ int run_net(const pde_net* net, int order, int mode, const pde_envelope* env, co
   r.grad = static_cast<T*>(grad);
   r.sums = (mode == MODE_PROGRAM) ? static_cast<T*>(sums) : nullptr;
   r.energy_grad = (mode == MODE_PROGRAM) ? static_cast<T*>(energy_grad) : nullptr;
+  if (ex) {
+    if (mode != MODE_PROGRAM || !r.grad || !r.sums || !r.energy_grad) return PDE_ERR_INVALID;
+    rc = comm_fill_args(ex->peers, sizeof(T) == 8 ? PDE_F64 : PDE_F32, p.n_params + 1 + a.n_q, ex->slot_elems, ex->seq, &r.comm);
+    if (rc) return rc;
+    r.have_comm = 1;
+  }
   if (launch_reduce<T>(st, r) != cudaSuccess) return PDE_ERR_CUDA;
   return PDE_OK;
 }
@@ -340,9 +346,10 @@ int pde_jets_backward(const pde_net* net, int32_t order, const void* X, int64_t 
                         grad, nullptr, workspace, workspace_bytes, st);
 }
 
-int pde_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
-                           int64_t n_points, const void* seed, double inv_n, void* sums, void* grad,
-                           void* energy_grad, void* workspace, size_t workspace_bytes, void* stream) {
+static int residual_loss_grad_impl(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
+                                   int64_t n_points, const void* seed, double inv_n, void* sums, void* grad,
+                                   void* energy_grad, void* workspace, size_t workspace_bytes, void* stream,
+                                   const ExchangeReq* ex) {
   if (!net || !prog) return PDE_ERR_INVALID;
   const int order = pde_program_order(prog->kind);
   if (order < 0) return PDE_ERR_INVALID;
@@ -353,13 +360,37 @@ int pde_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pd
   // Blackwell tensor-core path for the shapes it covers (fp32, H = 64 sin/tanh nets); it
   // declines with PDE_ERR_UNSUPPORTED and the generic SIMT kernel takes over.
   rc = pde::tc_residual_loss_grad(net, env, prog, X, n_points, seed, inv_n, sums, grad, energy_grad, workspace,
-                                  workspace_bytes, st);
+                                  workspace_bytes, st, ex);
   if (rc != PDE_ERR_UNSUPPORTED) return rc;
   if (net->dtype == PDE_F64)
     return run_net<double>(net, order, MODE_PROGRAM, env, prog, X, n_points, seed, inv_n, nullptr, nullptr, sums, grad,
-                           energy_grad, workspace, workspace_bytes, st);
+                           energy_grad, workspace, workspace_bytes, st, ex);
   return run_net<float>(net, order, MODE_PROGRAM, env, prog, X, n_points, seed, inv_n, nullptr, nullptr, sums, grad,
-                        energy_grad, workspace, workspace_bytes, st);
+                        energy_grad, workspace, workspace_bytes, st, ex);
+}
+
+int pde_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
+                           int64_t n_points, const void* seed, double inv_n, void* sums, void* grad,
+                           void* energy_grad, void* workspace, size_t workspace_bytes, void* stream) {
+  return residual_loss_grad_impl(net, env, prog, X, n_points, seed, inv_n, sums, grad, energy_grad, workspace,
+                                 workspace_bytes, stream, nullptr);
+}
+
+int pde_residual_loss_grad_exchange(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
+                                    int64_t n_points, const void* seed, double inv_n, void* result, void* workspace,
+                                    size_t workspace_bytes, const pde_peers* peers, int64_t slot_elems, void* seq,
+                                    void* stream) {
+  if (!net || !prog || !result || !peers || !seq) return PDE_ERR_INVALID;
+  int64_t np = 0;
+  int rc = pde_param_count(net, &np);
+  if (rc) return rc;
+  const int K = pde_program_quantities(prog->kind);
+  if (K < 1) return PDE_ERR_INVALID;
+  const size_t es = net->dtype == PDE_F64 ? 8 : 4;
+  unsigned char* base = static_cast<unsigned char*>(result);
+  ExchangeReq ex{peers, slot_elems, seq};
+  return residual_loss_grad_impl(net, env, prog, X, n_points, seed, inv_n, base + (size_t)(np + 1) * es, base,
+                                 base + (size_t)np * es, workspace, workspace_bytes, stream, &ex);
 }
 
 int pde_query_path(const pde_net* net, const pde_program* prog, int64_t n_points) {

@@ -36,125 +36,49 @@
 #include <atomic>
 
 #include "../../include/pde_b200.h"
+#include "pde_comm.cuh"
 
 namespace pde { void count_launch(int k); }   // pde_abi.cu: launch counter behind pde_launch_count()
 
 namespace {
 
-constexpr int CTRL_BYTES = 512;     // local control words in front of the slots: [0] block-completion counter, [16] timeouts
-constexpr int CTRL_ERR_WORD = 16;   // uint32 index of the error counter inside the control block
-std::atomic<long long> g_spin_limit{600ll * 2000000000ll};   // clock64 ticks; <= 0: no timeout
+using namespace pde::comm;
 constexpr int COMM_THREADS = 256, COMM_MAX_BLOCKS = 16;
+std::atomic<long long> g_spin_limit{600ll * 2000000000ll};   // clock64 ticks; <= 0: no timeout
 
-// (value, flag) travels as ONE 64-bit scalar access: single-copy atomic in the PTX memory model
-__device__ __forceinline__ void st_pair_sys(void* p, uint32_t v, uint32_t flag) {
-  const unsigned long long w = ((unsigned long long)flag << 32) | v;
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ uint2 ld_pair_sys(const void* p) {
-  unsigned long long w;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-  return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
-}
-
-struct CommArgs {
-  int rank, world;
-  unsigned char* base[PDE_MAX_PEERS];   // peer-visible allocation of every rank: [ctrl | parity 0: [W][slot] pairs | parity 1]
-  long long n_words, slot_words;        // 32-bit words of the vector / capacity of one slot
-  int is_f64;
-  void* buf;                            // local vector, reduced in place
-  uint32_t* seq;                        // local: number of completed calls
-  long long spin_limit;                 // clock64 ticks before giving up (a peer died): result is poisoned with NaN
-};
-
-__device__ __forceinline__ unsigned char* slot_of(unsigned char* base, int par, int src, long long slot_words) {
-  return base + CTRL_BYTES + ((size_t)par * PDE_MAX_PEERS + src) * (size_t)slot_words * 8;
-}
-
-// Thread = one element (one 32-bit word for float, two for double).
+// Thread = one element.
 template <typename T>
 __global__ void __launch_bounds__(COMM_THREADS) allreduce_oneshot_kernel(const CommArgs a) {
-  constexpr int WPE = sizeof(T) / 4;             // words per element
+  constexpr int WPE = sizeof(T) / 4;
   const uint32_t call = *a.seq + 1u;
-  const int par = (int)(call & 1u);
-  uint32_t* buf = static_cast<uint32_t*>(a.buf);
+  T* buf = static_cast<T*>(a.buf);
   const long long n = a.n_words / WPE;
-  unsigned char* my_slots = slot_of(a.base[a.rank], par, 0, a.slot_words);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    uint32_t w[WPE];
-#pragma unroll
-    for (int k = 0; k < WPE; ++k) w[k] = buf[i * WPE + k];
-    // push my words to every peer's slot [par][rank]
-#pragma unroll
-    for (int p = 0; p < PDE_MAX_PEERS; ++p) {
-      if (p < a.world && p != a.rank) {
-        unsigned char* dst = slot_of(a.base[p], par, a.rank, a.slot_words) + (size_t)i * WPE * 8;
-#pragma unroll
-        for (int k = 0; k < WPE; ++k) st_pair_sys(dst + 8 * k, w[k], call);
-      }
-    }
-    // pull: poll my local slots [par][p] until the flags carry this call's number
-    uint32_t got[PDE_MAX_PEERS][WPE];
-    uint32_t pending = 0;
-#pragma unroll
-    for (int p = 0; p < PDE_MAX_PEERS; ++p)
-      if (p < a.world && p != a.rank) pending |= 1u << p;
-    const long long t0 = clock64();
-    bool bad = false;
-    while (pending) {
-#pragma unroll
-      for (int p = 0; p < PDE_MAX_PEERS; ++p) {
-        if (pending & (1u << p)) {
-          const unsigned char* src = my_slots + (size_t)p * a.slot_words * 8 + (size_t)i * WPE * 8;
-          uint2 v[WPE];
-#pragma unroll
-          for (int k = 0; k < WPE; ++k) v[k] = ld_pair_sys(src + 8 * k);
-          bool ok = true;
-#pragma unroll
-          for (int k = 0; k < WPE; ++k) ok = ok && (v[k].y == call);
-          if (ok) {
-#pragma unroll
-            for (int k = 0; k < WPE; ++k) got[p][k] = v[k].x;
-            pending &= ~(1u << p);
-          }
-        }
-      }
-      if (pending && a.spin_limit > 0 && clock64() - t0 > a.spin_limit) { bad = true; break; }
-    }
-    // rank-ordered sum 0, 1, ..., W-1 on every rank
-    T acc = T(0);
-#pragma unroll
-    for (int p = 0; p < PDE_MAX_PEERS; ++p) {
-      if (p < a.world) {
-        T v;
-        if (p == a.rank) {
-          if (WPE == 1) v = (T)__uint_as_float(w[0]); else v = (T)__hiloint2double(w[WPE - 1], w[0]);
-        } else {
-          if (WPE == 1) v = (T)__uint_as_float(got[p][0]); else v = (T)__hiloint2double(got[p][WPE - 1], got[p][0]);
-        }
-        acc = (p == 0) ? v : acc + v;
-      }
-    }
-    if (bad) {
-      acc = (T)__longlong_as_double(0x7ff8000000000000ll);
-      atomicAdd(reinterpret_cast<uint32_t*>(a.base[a.rank]) + CTRL_ERR_WORD, 1u);   // seen by pde_exchange_errors()
-    }
-    static_cast<T*>(a.buf)[i] = acc;
-  }
-  // the last block to finish advances the call counter: by then every block has read it
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t* done = reinterpret_cast<uint32_t*>(a.base[a.rank]);
-    __threadfence();
-    if (atomicAdd(done, 1u) == gridDim.x - 1) {
-      *done = 0u;
-      __threadfence();
-      *a.seq = call;
-    }
-  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    buf[i] = exchange_element<T>(a, i, buf[i], call);
+  finish_call(a, call);
 }
 
 }  // namespace
+
+namespace pde {
+int comm_fill_args(const pde_peers* peers, int32_t dtype, int64_t n, int64_t slot_elems, void* seq, comm::CommArgs* out) {
+  if (!peers || !seq || !out) return PDE_ERR_INVALID;
+  if (dtype != PDE_F32 && dtype != PDE_F64) return PDE_ERR_INVALID;
+  if (peers->world < 1 || peers->world > PDE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return PDE_ERR_INVALID;
+  if (n < 1 || n > slot_elems) return PDE_ERR_INVALID;
+  comm::CommArgs& a = *out;
+  a.rank = peers->rank; a.world = peers->world;
+  for (int p = 0; p < PDE_MAX_PEERS; ++p) {
+    a.base[p] = p < peers->world ? static_cast<unsigned char*>(peers->base[p]) : nullptr;
+    if (p < peers->world && !a.base[p]) return PDE_ERR_INVALID;
+  }
+  const int wpe = dtype == PDE_F64 ? 2 : 1;
+  a.n_words = n * wpe; a.slot_words = slot_elems * wpe; a.is_f64 = dtype == PDE_F64;
+  a.buf = nullptr; a.seq = static_cast<uint32_t*>(seq);
+  a.spin_limit = g_spin_limit.load(std::memory_order_relaxed);
+  return PDE_OK;
+}
+}  // namespace pde
 
 extern "C" {
 
@@ -202,20 +126,11 @@ int pde_peer_bytes(int32_t dtype, int64_t slot_elems, size_t* bytes) {
 
 int pde_allreduce_oneshot(const pde_peers* peers, int32_t dtype, void* buf, int64_t n, int64_t slot_elems, void* seq,
                           void* stream) {
-  if (!peers || !buf || !seq) return PDE_ERR_INVALID;
-  if (dtype != PDE_F32 && dtype != PDE_F64) return PDE_ERR_INVALID;
-  if (peers->world < 1 || peers->world > PDE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return PDE_ERR_INVALID;
-  if (n < 1 || n > slot_elems) return PDE_ERR_INVALID;
+  if (!buf) return PDE_ERR_INVALID;
   CommArgs a;
-  a.rank = peers->rank; a.world = peers->world;
-  for (int p = 0; p < PDE_MAX_PEERS; ++p) {
-    a.base[p] = p < peers->world ? static_cast<unsigned char*>(peers->base[p]) : nullptr;
-    if (p < peers->world && !a.base[p]) return PDE_ERR_INVALID;
-  }
-  const int wpe = dtype == PDE_F64 ? 2 : 1;
-  a.n_words = n * wpe; a.slot_words = slot_elems * wpe; a.is_f64 = dtype == PDE_F64;
-  a.buf = buf; a.seq = static_cast<uint32_t*>(seq);
-  a.spin_limit = g_spin_limit.load(std::memory_order_relaxed);
+  int rc = pde::comm_fill_args(peers, dtype, n, slot_elems, seq, &a);
+  if (rc) return rc;
+  a.buf = buf;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long g = (n + COMM_THREADS - 1) / COMM_THREADS;
   const int grid = (int)(g < 1 ? 1 : (g > COMM_MAX_BLOCKS ? COMM_MAX_BLOCKS : g));

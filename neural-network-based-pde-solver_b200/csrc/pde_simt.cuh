@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pde_comm.cuh"
+
 namespace pde {
 
 enum Mode { MODE_JETS_FWD = 0, MODE_JETS_BWD = 1, MODE_PROGRAM = 2 };
@@ -674,11 +676,16 @@ struct ReduceArgs {
   T* grad;         // may be null
   T* sums;         // may be null
   T* energy_grad;  // may be null
+  // Exchange fused into the reduction (pde_residual_loss_grad_exchange): every reduced element is pushed to the peers
+  // and summed over the ranks before it is written; slot index = position in the caller's [grad | dE | sums] vector.
+  int have_comm;
+  comm::CommArgs comm;
 };
 
 template <typename T>
 __global__ void reduce_kernel(const ReduceArgs<T> a) {
   const long long total = a.n_params + a.n_q + 1;
+  const uint32_t call = a.have_comm ? *a.comm.seq + 1u : 0u;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long src = 0;
@@ -690,7 +697,9 @@ __global__ void reduce_kernel(const ReduceArgs<T> a) {
       const int col = (k < a.n_q) ? k : 4;
       double v = 0.0;
       for (int g = 0; g < a.grid; ++g) v += a.psums[(long long)g * 8 + col];
-      *dst = (T)v;
+      T r = (T)v;
+      if (a.have_comm) r = comm::exchange_element<T>(a.comm, (k < a.n_q) ? a.n_params + 1 + k : a.n_params, r, call);
+      *dst = r;
       continue;
     }
     {
@@ -720,8 +729,11 @@ __global__ void reduce_kernel(const ReduceArgs<T> a) {
     }
     double v = 0.0;
     for (int g = 0; g < a.grid; ++g) v += (double)a.partial[(long long)g * a.PP + src];
-    *dst = (T)v;
+    T r = (T)v;
+    if (a.have_comm) r = comm::exchange_element<T>(a.comm, i, r, call);
+    *dst = r;
   }
+  if (a.have_comm) comm::finish_call(a.comm, call);
 }
 
 }  // namespace pde

@@ -1562,8 +1562,9 @@ static cudaError_t launch_one(const TcPlan& p, const TcArgs& a, cudaStream_t st)
 
 template <int ACT>
 static cudaError_t launch_act(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
-#ifdef PDE_TC_ONLY_CFG2   // development builds (A/B timing of kernel variants): the headline instantiation only
+#ifdef PDE_TC_ONLY_CFG2   // development builds (A/B timing of kernel variants): configs 2 and 3 only
   if (p.D == 3 && p.order == 2 && ACT == 0) return launch_one<3, 2, 0>(p, a, st);
+  if (p.D == 5 && p.order == 1 && ACT == 0) return launch_one<5, 1, 0>(p, a, st);
   return cudaErrorInvalidValue;
 #else
   switch (p.D * 3 + p.order) {
@@ -1715,7 +1716,7 @@ int tc_workspace_bytes(const pde_net* net, int order, long long n_points, size_t
 // Shared launcher: parameter images, the fused kernel in `mode`, fixed-order reduction of the per-CTA partials.
 static int tc_run(const pde_net* net, int order, int mode, const pde_envelope* env, const pde_program* prog, const void* X,
                   long long n_points, const void* seed, double inv_n, void* J, const void* Jbar, void* sums, void* grad,
-                  void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                  void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st, const ExchangeReq* ex = nullptr) {
   using namespace tc;
   TcPlan p;
   int rc = make_plan(net, order, n_points, &p);
@@ -1785,19 +1786,25 @@ static int tc_run(const pde_net* net, int order, int mode, const pde_envelope* e
   r.grad = static_cast<float*>(grad);
   r.sums = (mode == 0) ? static_cast<float*>(sums) : nullptr;
   r.energy_grad = (mode == 0) ? static_cast<float*>(energy_grad) : nullptr;
+  if (ex) {
+    if (mode != 0 || !r.grad || !r.sums || !r.energy_grad) return PDE_ERR_INVALID;
+    rc = comm_fill_args(ex->peers, PDE_F32, p.n_params + 1 + a.n_q, ex->slot_elems, ex->seq, &r.comm);
+    if (rc) return rc;
+    r.have_comm = 1;
+  }
   if (launch_reduce<float>(st, r) != cudaSuccess) return PDE_ERR_CUDA;
   return PDE_OK;
 }
 
 int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
                           long long n_points, const void* seed, double inv_n, void* sums, void* grad,
-                          void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                          void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st, const ExchangeReq* ex) {
   if (!net || !prog) return PDE_ERR_INVALID;
   const int order = pde_program_order(prog->kind);
   if (order < 0) return PDE_ERR_INVALID;
   if (!program_ok(prog)) return PDE_ERR_UNSUPPORTED;
   return tc_run(net, order, 0, env, prog, X, n_points, seed, inv_n, nullptr, nullptr, sums, grad, energy_grad, workspace,
-                workspace_bytes, st);
+                workspace_bytes, st, ex);
 }
 
 // Network jets on the tensor-core kernel (orders 0 and 1, whose channels are the ABI's): what the WAN losses

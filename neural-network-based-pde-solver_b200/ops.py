@@ -220,6 +220,7 @@ def _points(X):
 
 
 _EXCHANGE = {}   # process group -> comm.NvlinkAllReduce registered by use_nvlink_exchange
+FUSE_EXCHANGE = True   # fold the exchange into the reduction launch (False: separate pde_allreduce_oneshot launch)
 
 
 def use_nvlink_exchange(group=None, max_elems=1 << 17, dtype=torch.float32):
@@ -233,10 +234,21 @@ def use_nvlink_exchange(group=None, max_elems=1 << 17, dtype=torch.float32):
     return _EXCHANGE[key]
 
 
+def _exchange_for(t, group):
+    """The registered NVLink communicator that can carry ``t`` for ``group`` (None: use NCCL)."""
+    if not _EXCHANGE or group is None:
+        return None
+    import torch.distributed as dist
+    ar = _EXCHANGE.get((group if group is not None else dist.group.WORLD, t.dtype))
+    if ar is not None and t.is_cuda and t.is_contiguous() and t.numel() <= ar.slot:
+        return ar
+    return None
+
+
 def _all_reduce(t, group):
     import torch.distributed as dist
-    ar = _EXCHANGE.get((group if group is not None else dist.group.WORLD, t.dtype)) if _EXCHANGE else None
-    if ar is not None and t.is_cuda and t.is_contiguous() and t.numel() <= ar.slot:
+    ar = _exchange_for(t, group)
+    if ar is not None:
         ar.all_reduce_(t)
     else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -347,11 +359,19 @@ class _Residual(torch.autograd.Function):
         gptr = buf.data_ptr() if fused else None
         eptr = buf.data_ptr() + nparam * buf.element_size() if fused else None
         sptr = buf.data_ptr() + (nparam + 1) * buf.element_size()
+        ar = _exchange_for(buf, group) if (fused and FUSE_EXCHANGE) else None
         with torch.cuda.device(dev), _timed(dev):
-            L.check(lib.pde_residual_loss_grad(C.byref(cnet), C.byref(cenv), C.byref(prog), X.data_ptr(), n, None,
-                                               1.0 / n_tot, sptr, gptr, eptr, ws.data_ptr(), ws.numel(), _stream(dev)),
-                    "pde_residual_loss_grad")
-        means = combine_forward(buf, nparam, n_tot, group, fused)
+            if ar is not None:
+                # exchange folded into the reduction of the per-CTA partials: no separate all-reduce launch
+                L.check(lib.pde_residual_loss_grad_exchange(C.byref(cnet), C.byref(cenv), C.byref(prog), X.data_ptr(), n, None,
+                                                            1.0 / n_tot, buf.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                            C.byref(ar.peers), ar.slot, ar.seq.data_ptr(), _stream(dev)),
+                        "pde_residual_loss_grad_exchange")
+            else:
+                L.check(lib.pde_residual_loss_grad(C.byref(cnet), C.byref(cenv), C.byref(prog), X.data_ptr(), n, None,
+                                                   1.0 / n_tot, sptr, gptr, eptr, ws.data_ptr(), ws.numel(), _stream(dev)),
+                        "pde_residual_loss_grad")
+        means = combine_forward(buf, nparam, n_tot, None if ar is not None else group, fused)
         ctx.fused = fused
         ctx.has_energy = energy is not None
         if fused:
@@ -410,6 +430,15 @@ class _Residual(torch.autograd.Function):
         return tuple(out)
 
 
+def _global_count(n, group, n_global):
+    """Points of the global batch: with ``group`` and no explicit ``n_global`` every rank is taken to hold ``n``
+    points (dividing the all-reduced sums by the local count would make loss and gradient world times too large)."""
+    if n_global is not None or group is None:
+        return n_global
+    import torch.distributed as dist
+    return n * dist.get_world_size(group)
+
+
 def residual_means(model, X, spec: ProgramSpec, env: EnvelopeSpec = NO_ENVELOPE, f=None, beta=None, energy=None,
                    group=None, n_global: Optional[int] = None) -> torch.Tensor:
     """Means of the program's per-point quantities, differentiable w.r.t. the network parameters
@@ -417,6 +446,7 @@ def residual_means(model, X, spec: ProgramSpec, env: EnvelopeSpec = NO_ENVELOPE,
     X = _points(X)
     net = _Net(model, X)
     n = X.shape[0]
+    n_global = _global_count(n, group, n_global)
 
     def coef(t):
         if t is None:
@@ -533,6 +563,7 @@ def wan_means(u_model, v_model, X, spec: WanSpec, env_u=NO_ENVELOPE, env_v=NO_EN
     """
     X = _points(X)
     n = X.shape[0]
+    n_global = _global_count(n, group, n_global)
 
     def coef(t):
         if t is None:

@@ -25,20 +25,31 @@ def V_KH(x, alpha=0.0, V0=-24.856, use_avg=True, n_theta=500):
     return V_base(x[..., None] + alpha * sin_th[None, ...], V0).mean(dim=-1)
 
 
-_V_CACHE = {}
+_V_CACHE = []   # [(weakref to the grid tensor, its _version, (alpha, V0, use_avg, n_theta), V)]
 
 
 def _potential(x, alpha, V0, use_avg, n_theta):
     """The potential depends on neither the parameters nor the epoch; the reference rebuilds an
-    (N, n_theta) tensor in every loss call (KH_1D.py:231,239,259) — here it is computed once per grid."""
-    key = (x.data_ptr(), x._version, tuple(x.shape), x.dtype, float(alpha), float(V0), bool(use_avg), int(n_theta))
-    V = _V_CACHE.get(key)
-    if V is None:
-        if len(_V_CACHE) > 16:
-            _V_CACHE.clear()
-        with torch.no_grad():
-            V = V_KH(x.detach(), alpha=alpha, V0=V0, use_avg=use_avg, n_theta=n_theta)
-        _V_CACHE[key] = V
+    (N, n_theta) tensor in every loss call (KH_1D.py:231,239,259) — here it is computed once per grid.
+    An entry is reused only for the very same tensor object at the same version: storage addresses are
+    recycled by the caching allocator, so they cannot identify a grid."""
+    import weakref
+    cfg = (float(alpha), float(V0), bool(use_avg), int(n_theta))
+    alive = []
+    hit = None
+    for ref, ver, c, V in _V_CACHE:
+        t = ref()
+        if t is None:
+            continue
+        alive.append((ref, ver, c, V))
+        if t is x and ver == x._version and c == cfg:
+            hit = V
+    _V_CACHE[:] = alive[-16:]
+    if hit is not None:
+        return hit
+    with torch.no_grad():
+        V = V_KH(x.detach(), alpha=alpha, V0=V0, use_avg=use_avg, n_theta=n_theta)
+    _V_CACHE.append((weakref.ref(x), x._version, cfg, V))
     return V
 
 

@@ -95,7 +95,10 @@ def test_trainer_matches_reference_loop(method, bc, dim, graph):
     X = torch.rand(N, dim, dtype=torch.float64) * L
     f = pb.poisson.rhs_f_for_u_sin(X, L, ks)
     want = _reference_loop(m_cpu, X, f, L, bc, method.lower(), lr, epochs)
-    tr = pb.train.FusedTrainer(m_gpu, L, ks, method=method, lr=lr, X=X.cuda(), f=f.cuda(), history=epochs, graph=graph)
+    # PDE term only: an 'RB' model with weights={'bc': 0} is the raw network without boundary term (the natural-BC
+    # reading of BASELINE config 3); the reference's own default for 'RB' is bc = 1e4 (covered further down)
+    tr = pb.train.FusedTrainer(m_gpu, L, ks, method=method, lr=lr, X=X.cuda(), f=f.cuda(), history=epochs, graph=graph,
+                               weights={"bc": 0.0})
     tr.step(epochs)
     got = tr.hist_loss.cpu().numpy()
     np.testing.assert_allclose(got, np.array(want), rtol=1e-9, atol=1e-12)
@@ -220,3 +223,126 @@ def test_graphed_wan_epoch_matches_eager():
     for a, b in zip(list(um1.parameters()) + list(vm1.parameters()), list(um2.parameters()) + list(vm2.parameters())):
         assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
     assert abs(float(t1) - float(t2)) <= 1e-5 * max(1e-3, abs(float(t1)))
+
+
+# ---------------------------------------------------------------- the rest of the reference epoch (Poisson_ND.py:224-276)
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("method,norm_mode", [("PINN", "nontrivial"), ("DRM", "l2")])
+def test_trainer_rb_bc_data_norm_terms_match_reference_loop(method, norm_mode, graph):
+    """RB branch with the soft Dirichlet penalty on freshly drawn face points, the data term and the norm term
+    (Poisson_ND.py:224-239): five epochs of the fused trainer equal the reference loop (oracle nested-autograd losses +
+    torch.optim.Adam, float64 on the CPU) run on the face points the trainer drew."""
+    import copy
+    torch.manual_seed(11)
+    L, ks, dim, n, nd, epochs = 2.0, [1, 2], 2, 1500, 120, 5
+    w = {"pde": 1.0, "bc": 50.0, "data": 20.0, "norm": 0.3}
+    model = pb.poisson.SolutionNet(dim, 24, 4, "RB").double()
+    ref = copy.deepcopy(model)
+    model = model.cuda()
+    X = torch.rand(n, dim, dtype=torch.float64) * L
+    f = pb.poisson.rhs_f_for_u_sin(X, L, ks)
+    Xd = torch.rand(nd, dim, dtype=torch.float64) * L
+    ud = pb.poisson.exact_u_prod_sin(Xd, L, ks)
+    tr = pb.train.FusedTrainer(model, L, ks, method=method, X=X.cuda(), f=f.cuda(), lr=2e-3, weights=w, n_boundary=400,
+                               X_data=Xd.cuda(), u_data=ud.cuda(), norm_mode=norm_mode, graph=graph, seed=5)
+    faces, terms = [], []
+    for _ in range(epochs):
+        tr.step(1)
+        faces.append(tr.Xb.detach().cpu().clone())
+        terms.append({k: float(v) for k, v in tr.terms.items()})
+    # reference loop on the same face points
+    opt = torch.optim.Adam(ref.parameters(), lr=2e-3)
+    for ep in range(epochs):
+        opt.zero_grad()
+        Xr = X.clone().requires_grad_(True)
+        pde = (AR.pinn_loss if method == "PINN" else AR.drm_loss)(ref.net, Xr, f, L, "RB")
+        bc = torch.mean(ref(faces[ep], L) ** 2)                 # equal face counts: mean of face means = overall mean
+        data = torch.mean((ref(Xd, L) - ud) ** 2)
+        nrm = pb.poisson.norm_loss(ref(X, L), mode=norm_mode)
+        total = w["pde"] * pde + w["bc"] * bc + w["data"] * data + w["norm"] * nrm
+        for got, want, nm in ((terms[ep]["pde"], pde, "pde"), (terms[ep]["bc"], bc, "bc"), (terms[ep]["data"], data, "data"),
+                              (terms[ep]["norm"], nrm, "norm"), (terms[ep]["total"], total, "total")):
+            assert abs(got - float(want)) <= 1e-9 * max(1.0, abs(float(want))), (ep, nm, got, float(want))
+        total.backward(); opt.step()
+    for a, b in zip(model.parameters(), ref.parameters()):
+        assert float((a.detach().cpu() - b.detach()).abs().max()) <= 1e-9 * max(1.0, float(b.detach().abs().max()))
+    # the face draw: 2d faces with equal counts, the face coordinate exactly 0 or L, the others inside [0, L)
+    Xb = faces[-1].view(2 * dim, -1, dim)
+    for k in range(2 * dim):
+        assert torch.all(Xb[k, :, k // 2] == (L if k % 2 else 0.0))
+    assert float(faces[-1].min()) >= 0.0 and float(faces[-1].max()) <= L and not torch.equal(faces[0], faces[1])
+    with pytest.raises(ValueError):
+        pb.train.FusedTrainer(model, L, ks, weights={"bogus": 1.0})
+    with pytest.raises(ValueError):
+        pb.train.FusedTrainer(model, L, ks, weights={"data": 1.0})      # data weight without data points
+
+
+def test_trainer_default_weights_follow_reference():
+    """weights default like Poisson_ND.py:169-173: bc 1e4 for an 'RB' model (soft constraint), 0 for 'FBC'."""
+    m = pb.poisson.SolutionNet(2, 16, 3, "RB").cuda()
+    tr = pb.train.FusedTrainer(m, 2.0, [1, 1], n_interior=512, graph=False)
+    assert tr.w["bc"] == 1e4 and tr.use["bc"] and tr.w["data"] == 0.0 and not tr.use["norm"]
+    tr.step(2)
+    assert float(tr.terms["bc"]) > 0.0 and math.isfinite(float(tr.terms["total"]))
+    m2 = pb.poisson.SolutionNet(2, 16, 3, "FBC").cuda()
+    tr2 = pb.train.FusedTrainer(m2, 2.0, [1, 1], n_interior=512, graph=False)
+    assert tr2.w["bc"] == 0.0 and tr2.rows == ["pde"]
+
+
+def test_wan_trainer_matches_reference_loop():
+    """The WAN branch of the reference epoch (Poisson_ND.py:242-276: critic_steps critic updates and one solution
+    update per epoch, every evaluation on freshly drawn points): four epochs of WanTrainer (drop-in wan_losses on the
+    fused kernels + torch Adam) equal the reference loop (oracle nested-autograd wan_losses + torch.optim.Adam, float64
+    on the CPU) run on the points the trainer drew."""
+    import copy
+    torch.manual_seed(13)
+    L, ks, dim, n, epochs, csteps, reg = 2.0, [1, 1], 2, 800, 4, 3, 0.7
+    w = {"pde": 1.0, "bc": 30.0, "data": 5.0, "norm": 0.2}
+    um = pb.poisson.SolutionNet(dim, 24, 4, "RB").double()
+    vm = pb.poisson.CriticNet(dim, 16, 3).double()
+    ur, vr = copy.deepcopy(um), copy.deepcopy(vm)
+    um, vm = um.cuda(), vm.cuda()
+    Xd = torch.rand(60, dim, dtype=torch.float64) * L
+    ud = pb.poisson.exact_u_prod_sin(Xd, L, ks)
+    tr = pb.train.WanTrainer(um, vm, L, ks, n_interior=n, lr=2e-3, critic_steps=csteps, wan_reg=reg, weights=w, n_boundary=200,
+                             X_data=Xd.cuda(), u_data=ud.cuda(), norm_mode="l2", seed=3, graph=False, record_points=True)
+    hist = []
+    for _ in range(epochs):
+        tr.step(1)
+        hist.append({k: float(v) for k, v in tr.last.items()})
+    draws = iter(tr.drawn)
+    opt_u = torch.optim.Adam(ur.parameters(), lr=2e-3)
+    opt_v = torch.optim.Adam(vr.parameters(), lr=2e-3)
+    for ep in range(epochs):
+        for _ in range(csteps):
+            kind, Xc, fc = next(draws); assert kind == "v"
+            Xc = Xc.cpu().requires_grad_(True)
+            _, lv, _, _ = AR.wan_losses(ur.net, vr.net, Xc, fc.cpu(), L, "RB", v_reg_weight=reg)
+            opt_v.zero_grad(); lv.backward(); opt_v.step()
+        kind, Xu, fu = next(draws); assert kind == "u"
+        Xu = Xu.cpu().requires_grad_(True)
+        lpde, _, weak, pn = AR.wan_losses(ur.net, vr.net, Xu, fu.cpu(), L, "RB", v_reg_weight=reg)
+        kind, Xb, _ = next(draws); assert kind == "bc"
+        bc = torch.mean(ur(Xb.cpu(), L) ** 2)
+        data = torch.mean((ur(Xd, L) - ud) ** 2)
+        nrm = pb.poisson.norm_loss(ur(Xu.detach(), L), mode="l2")
+        total = w["pde"] * lpde + w["bc"] * bc + w["data"] * data + w["norm"] * nrm
+        for nm, want in (("pde", lpde), ("bc", bc), ("data", data), ("norm", nrm), ("total", total), ("wan_loss_v", lv),
+                         ("wan_weak", weak), ("wan_phi_norm", pn)):
+            assert abs(hist[ep][nm] - float(want)) <= 1e-9 * max(1.0, abs(float(want))), (ep, nm, hist[ep][nm], float(want))
+        opt_u.zero_grad(); total.backward(); opt_u.step()
+    for a, b in zip(list(um.parameters()) + list(vm.parameters()), list(ur.parameters()) + list(vr.parameters())):
+        assert float((a.detach().cpu() - b.detach()).abs().max()) <= 1e-9 * max(1.0, float(b.detach().abs().max()))
+
+
+def test_wan_trainer_graph_replays_draw_fresh_points():
+    """Captured WAN epoch: every replay draws new points (device draw counter) and keeps training."""
+    torch.manual_seed(2)
+    um = pb.poisson.SolutionNet(2, 16, 3, "FBC").cuda()
+    vm = pb.poisson.CriticNet(2, 16, 3).cuda()
+    tr = pb.train.WanTrainer(um, vm, 2.0, [1, 1], n_interior=2048, critic_steps=2, graph=True)
+    tr.step(1)
+    X1 = tr.bufs[-1][0].detach().clone(); d1 = int(tr.draws)
+    tr.step(3)
+    assert int(tr.draws) == d1 + 3 * 3 and not torch.equal(X1, tr.bufs[-1][0].detach())
+    assert all(math.isfinite(float(v)) for v in tr.last.values())

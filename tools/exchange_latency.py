@@ -49,6 +49,29 @@ print("oneshot done", res, file=sys.stderr, flush=True)
 buf.normal_()
 g1 = graphed(lambda: ar.all_reduce_(buf))
 res["nvlink_oneshot_graphed_us"] = timed(g1, reps=30, inner=1) / 20
+# the whole data-parallel loss step at a latency-bound size (8192 points, config-2 network): exchange folded into the
+# reduction launch vs a separate one-kernel all-reduce vs NCCL
+from pde_b200 import ops
+torch.manual_seed(0)
+m = pb.poisson.SolutionNet(3, 64, 5, "FBC").cuda()
+Xs = torch.rand(8192, 3, device="cuda") * 2
+fs = pb.poisson.rhs_f_for_u_sin(Xs, 2.0, [1, 1, 1])
+
+
+def loss_step():
+    for p in m.parameters():
+        p.grad = None
+    pb.poisson.pinn_residual_loss(m, Xs, fs, 2.0, group=dist.group.WORLD).backward()
+
+
+res["step_nccl_us"] = timed(loss_step, reps=20, inner=10)
+ops._EXCHANGE[(dist.group.WORLD, torch.float32)] = ar
+ops.FUSE_EXCHANGE = False
+res["step_separate_oneshot_us"] = timed(loss_step, reps=20, inner=10)
+ops.FUSE_EXCHANGE = True
+res["step_fused_exchange_us"] = timed(loss_step, reps=20, inner=10)
+ar.check()
+ops._EXCHANGE.clear()
 if rank == 0:
     print(json.dumps(res))
 ar.close()
