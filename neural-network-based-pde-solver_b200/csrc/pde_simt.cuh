@@ -680,6 +680,8 @@ struct ReduceArgs {
   // and summed over the ranks before it is written; slot index = position in the caller's [grad | dE | sums] vector.
   int have_comm;
   comm::CommArgs comm;
+  int psum_grid;    // rows of psums (0: same as grid) — the dimension-split PINN step takes them from its pointwise kernel
+  int accumulate;   // add the reduced gradient to what grad already holds (second pass of that step)
 };
 
 template <typename T>
@@ -696,7 +698,8 @@ __global__ void reduce_kernel(const ReduceArgs<T> a) {
       if (!dst) continue;
       const int col = (k < a.n_q) ? k : 4;
       double v = 0.0;
-      for (int g = 0; g < a.grid; ++g) v += a.psums[(long long)g * 8 + col];
+      const int pg = a.psum_grid > 0 ? a.psum_grid : a.grid;
+      for (int g = 0; g < pg; ++g) v += a.psums[(long long)g * 8 + col];
       T r = (T)v;
       if (a.have_comm) r = comm::exchange_element<T>(a.comm, (k < a.n_q) ? a.n_params + 1 + k : a.n_params, r, call);
       *dst = r;
@@ -730,6 +733,7 @@ __global__ void reduce_kernel(const ReduceArgs<T> a) {
     double v = 0.0;
     for (int g = 0; g < a.grid; ++g) v += (double)a.partial[(long long)g * a.PP + src];
     T r = (T)v;
+    if (a.accumulate) r += *dst;
     if (a.have_comm) r = comm::exchange_element<T>(a.comm, i, r, call);
     *dst = r;
   }

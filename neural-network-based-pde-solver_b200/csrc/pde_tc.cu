@@ -93,6 +93,7 @@ struct TcArgs {
   float4* stash;                // [grid][stash_f4]
   long long PP, stash_f4, off_gW0, off_gb0, off_gW, off_gwL, off_gbL;
   long long* dbg;               // timeline buffer (builds with -DPDE_TC_TIMELINE only), else null
+  int dir0;                     // first derivative direction (dimension-split instantiations differentiate along dir0 .. dir0+NDIR-1)
   int mode;                     // 0: envelope + residual program; 1: network jets out (forward only); 2: jet cotangents in
   float* J;                     // mode 1: (n, C) network jets (value, first derivatives) out
   const float* Jbar;            // mode 2: (n, C) cotangents of the network jets in
@@ -444,9 +445,14 @@ __device__ __forceinline__ bool elect_one() {
 //   bar_w         commit       issuer -> epilogue : every MMA that reads the operand sets has completed
 // Accumulator regions ping-pong (R0/R1) so that the MMAs of step s+1 run while step s is still
 // being read; a step's K-step-j MMAs are issued as soon as chunk j has been written.
-template <int D, int ORDER, int ACT>
+// NDIR < D: dimension-split instantiation — jets along the NDIR directions dir0 .. dir0+NDIR-1 only (value, NDIR first
+// derivatives, the partial Laplacian over those directions); jet modes only.  The 5-D PINN step, whose 7 channels do
+// not fit on chip, is two such passes (3 + 2 directions) around a pointwise residual kernel (tc_pinn_split).
+template <int D, int ORDER, int ACT, int NDIR = D>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
-  constexpr int ND = (ORDER >= 1) ? D : 0;
+  constexpr int ND = (ORDER >= 1) ? NDIR : 0;
+  constexpr bool SPLIT = (NDIR != D);
+  const int dir0 = SPLIT ? a.dir0 : 0;
   constexpr int LAP = (ORDER == 2) ? 1 : 0;
   constexpr int C = 1 + ND + LAP;
   constexpr int NV = 2 + ND + LAP;  // stashed values per (point, unit, layer)
@@ -675,7 +681,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int i = 0; i < ND; ++i) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M + (2 * (1 + i) + 1) * TD + 128 * ks, DESC_HI, kETK + 64 * i + 2 * ks, DESC_HI, ID_SM, 1u);
+                mma_k(d, kT2M + (2 * (1 + i) + 1) * TD + 128 * ks, DESC_HI, kETK + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);
             }
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
@@ -683,7 +689,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int i = 0; i < ND; ++i) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK + 64 * i + 2 * ks, DESC_HI, ID_SM, 1u);
+                mma_k(d, kT2M + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);   // E tile of direction dir0 + i: column dir0 + i of gW0
             }
             mma_commit(bar_w);
           }
@@ -928,7 +934,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int jd = 0; jd < D; ++jd) v = fmaf(sW0t[jd * 64 + u], xr[e >> 1][jd], v);
               z[0][e] = v;
 #pragma unroll
-              for (int i = 0; i < ND; ++i) z[1 + i][e] = sW0t[i * 64 + u];
+              for (int i = 0; i < ND; ++i) z[1 + i][e] = sW0t[(dir0 + i) * 64 + u];
               if constexpr (LAP) z[1 + ND][e] = 0.f;
             }
           } else {
@@ -1060,8 +1066,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         for (int c = 0; c < C; ++c) nj[c] = sRed[tid * C + c] + sRed[(64 + tid) * C + c];
         nj[0] += sWL[64];
         bool programmed = false;
-        if constexpr (ORDER <= 1) {
-          // jet modes (pde_jets_forward / pde_jets_backward): for order <= 1 the kernel's channels are the ABI's
+        if constexpr (ORDER <= 1 || SPLIT) {
+          // jet modes (pde_jets_forward / pde_jets_backward): for order <= 1 the kernel's channels are the ABI's; the
+          // dimension-split passes exchange (value, NDIR derivatives, partial Laplacian)
           if (a.mode == 1) {
             if (gp < a.n) {
 #pragma unroll
@@ -1075,11 +1082,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
         }
         if (!programmed) {
-          if (gp < a.n) {
-            program_point_lap<D, ORDER>(a, sX + tid * D, fv, bt, nj, qs, gE);
+          if constexpr (!SPLIT) {
+            if (gp < a.n) {
+              program_point_lap<D, ORDER>(a, sX + tid * D, fv, bt, nj, qs, gE);
+            } else {
+#pragma unroll
+              for (int c = 0; c < C; ++c) nj[c] = 0.f;
+            }
           } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) nj[c] = 0.f;
+            for (int c = 0; c < C; ++c) nj[c] = 0.f;   // split instantiations run in the jet modes only
           }
         }
       }
@@ -1214,7 +1226,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int e = 0; e < NE; ++e) {
                 const int u = u0 + (e & 1);
 #pragma unroll
-                for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[i * 64 + u];
+                for (int i = 0; i < ND; ++i) zj[1 + i][e] = sW0t[(dir0 + i) * 64 + u];
                 if constexpr (LAP) zj[1 + ND][e] = 0.f;
               }
             }
@@ -1331,7 +1343,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int e = 0; e < NE; ++e) {
                 const int u = u0 + (e & 1);
 #pragma unroll
-                for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[i * 64 + u];
+                for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[(dir0 + i) * 64 + u];
                 if constexpr (LAP) zp[1 + ND][e] = 0.f;
               }
             }
@@ -1490,6 +1502,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------- 5-D PINN: residual stage between the two split passes
+// Per point: network jets of the two dimension-split forward passes (J_A: value, d_0..d_2, Lap over dims 0..2;
+// J_B: value, d_3, d_4, Lap over dims 3..4) -> envelope, residual program and per-point seeds exactly as in the fused
+// kernel (program_point_lap on (value, 5 derivatives, full Laplacian)) -> cotangents of both passes.  HBM-bound:
+// 4 (5 + 2 + 9 + 9) bytes per point, coalesced, grid = 4 x SMs.
+__global__ void pinn_split_kernel(const TcArgs a, const float* JA, const float* JB, float* JbarA, float* JbarB, double* psums) {
+  double qs[4] = {0.0, 0.0, 0.0, 0.0};
+  double gE = 0.0;
+  for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < a.n; gp += (long long)gridDim.x * blockDim.x) {
+    float x[5], nj[7];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) x[i] = a.X[gp * 5 + i];
+    nj[0] = JA[gp * 5];
+    nj[1] = JA[gp * 5 + 1]; nj[2] = JA[gp * 5 + 2]; nj[3] = JA[gp * 5 + 3];
+    nj[4] = JB[gp * 4 + 1]; nj[5] = JB[gp * 4 + 2];
+    nj[6] = JA[gp * 5 + 4] + JB[gp * 4 + 3];
+    const float fv = a.f ? a.f[gp] : 0.f;
+    const float bt = a.beta ? a.beta[gp] : a.beta_const;
+    program_point_lap<5, 2>(a, x, fv, bt, nj, qs, gE);
+    if (JbarA) {
+      // the value channel's cotangent goes to pass A only (the reverse sweep is linear in the cotangents)
+      JbarA[gp * 5] = nj[0]; JbarA[gp * 5 + 1] = nj[1]; JbarA[gp * 5 + 2] = nj[2]; JbarA[gp * 5 + 3] = nj[3]; JbarA[gp * 5 + 4] = nj[6];
+      JbarB[gp * 4] = 0.f; JbarB[gp * 4 + 1] = nj[4]; JbarB[gp * 4 + 2] = nj[5]; JbarB[gp * 4 + 3] = nj[6];
+    }
+  }
+  __shared__ double sh[8][5];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    double v = (k < 4) ? qs[k] : gE;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += sh[i][threadIdx.x];
+    psums[(long long)blockIdx.x * 8 + threadIdx.x] = v;
+  }
+}
+
 // ---------------------------------------------------------------- parameter images
 struct TcPackArgs {
   const float* W[PDE_MAX_LINEAR];
@@ -1539,6 +1592,7 @@ __global__ void tc_pack_kernel(const TcPackArgs a) {
 // ---------------------------------------------------------------- host side
 struct TcPlan {
   int D, order, C, NV, n_lin, n_h, H, grid, num_tiles, sms;
+  int ndir;   // derivative directions of this launch (= D except in the dimension-split passes)
   size_t smem_bytes;
   long long PP, off_gW0, off_gb0, off_gW, off_gwL, off_gbL, n_params, stash_f4;
   size_t ws_params, ws_wimg, ws_partial, ws_psums, ws_stash, ws_total;
@@ -1546,22 +1600,29 @@ struct TcPlan {
 
 static inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
 
-template <int D, int ORDER, int ACT>
+template <int D, int ORDER, int ACT, int NDIR = D>
 static cudaError_t launch_one(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
-  constexpr int C = 1 + (ORDER >= 1 ? D : 0) + (ORDER == 2);
+  constexpr int C = 1 + (ORDER >= 1 ? NDIR : 0) + (ORDER == 2);
   if constexpr (C > MAXC) {
     return cudaErrorInvalidValue;
   } else {
     const int smem = SmemMap<D, C>::total;
-    cudaError_t err = cudaFuncSetAttribute(tc_kernel<D, ORDER, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t err = cudaFuncSetAttribute(tc_kernel<D, ORDER, ACT, NDIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
-    tc_kernel<D, ORDER, ACT><<<p.grid, NTHREADS, smem, st>>>(a);
+    tc_kernel<D, ORDER, ACT, NDIR><<<p.grid, NTHREADS, smem, st>>>(a);
     return cudaGetLastError();
   }
 }
 
 template <int ACT>
 static cudaError_t launch_act(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
+  if (p.ndir != p.D) {   // dimension-split passes of the 5-D PINN step
+#ifndef PDE_TC_ONLY_CFG2
+    if (p.D == 5 && p.order == 2 && p.ndir == 3) return launch_one<5, 2, ACT, 3>(p, a, st);
+    if (p.D == 5 && p.order == 2 && p.ndir == 2) return launch_one<5, 2, ACT, 2>(p, a, st);
+#endif
+    return cudaErrorInvalidValue;
+  }
 #ifdef PDE_TC_ONLY_CFG2   // development builds (A/B timing of kernel variants): configs 2 and 3 only
   if (p.D == 3 && p.order == 2 && ACT == 0) return launch_one<3, 2, 0>(p, a, st);
   if (p.D == 5 && p.order == 1 && ACT == 0) return launch_one<5, 1, 0>(p, a, st);
@@ -1629,7 +1690,7 @@ static void timeline_dump(long long* buf, cudaStream_t st) {
 }
 #endif
 
-static bool shape_ok(const pde_net* net, int order, long long n) {
+static bool shape_ok(const pde_net* net, int order, long long n, int ndir = -1) {
   if (!net || net->dtype != PDE_F32) return false;
   if (net->dim < 1 || net->dim > PDE_MAX_DIM) return false;
   const int n_h = net->n_linear - 1;
@@ -1640,7 +1701,7 @@ static bool shape_ok(const pde_net* net, int order, long long n) {
     if (net->widths[l] != H) return false;
   if (net->widths[0] != net->dim || net->widths[net->n_linear] != 1) return false;
   if (order < 0 || order > 2) return false;
-  const int C = 1 + (order >= 1 ? net->dim : 0) + (order == 2);
+  const int C = 1 + (order >= 1 ? (ndir < 0 ? net->dim : ndir) : 0) + (order == 2);
   if (C > MAXC) return false;
   const int ov = path_override();
   if (ov == 0) return false;
@@ -1648,8 +1709,8 @@ static bool shape_ok(const pde_net* net, int order, long long n) {
   return n >= 4096;   // below that the launch is latency bound and the generic kernel is as fast
 }
 
-static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl) {
-  if (!shape_ok(net, order, n)) return PDE_ERR_UNSUPPORTED;
+static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl, int ndir = -1) {
+  if (!shape_ok(net, order, n, ndir)) return PDE_ERR_UNSUPPORTED;
   static std::atomic<int> sms_cached[64];   // per device ordinal
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return PDE_ERR_NO_DEVICE; }
@@ -1666,7 +1727,8 @@ static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl) {
   memset(&p, 0, sizeof(p));
   p.sms = sms_dev;
   p.D = net->dim; p.order = order;
-  p.C = 1 + (order >= 1 ? p.D : 0) + (order == 2);
+  p.ndir = ndir < 0 ? p.D : ndir;
+  p.C = 1 + (order >= 1 ? p.ndir : 0) + (order == 2);
   p.NV = 1 + p.C;
   p.n_lin = net->n_linear; p.n_h = p.n_lin - 1; p.H = net->widths[1];
   p.num_tiles = (int)((n + TP - 1) / TP);
@@ -1698,14 +1760,51 @@ static bool program_ok(const pde_program* prog) {
   return prog && (prog->kind != PDE_PROG_RAYLEIGH || tc::path_override() == 1);
 }
 
+// 5-D second-order programs need 7 jet channels, one more than fits on chip: they run as two dimension-split passes
+// (3 + 2 directions, 5 and 4 channels) around a pointwise residual kernel (tc_pinn_split below).
+static bool split_shape(const pde_net* net, int order) { return net && net->dim == 5 && order == 2; }
+constexpr int SPLIT_BLOCK = 256;
+struct SplitPlan {
+  tc::TcPlan a, b;          // passes over directions 0..2 and 3..4
+  int blocks;               // pointwise kernel
+  size_t ws_common, off_JA, off_JB, off_JbA, off_JbB, off_ps, ws_total;
+};
+static int make_split_plan(const pde_net* net, long long n, SplitPlan* sp) {
+  int rc = tc::make_plan(net, 2, n, &sp->a, 3);
+  if (rc) return rc;
+  if ((rc = tc::make_plan(net, 2, n, &sp->b, 2))) return rc;
+  long long g = (n + SPLIT_BLOCK - 1) / SPLIT_BLOCK;
+  sp->blocks = (int)(g < 4LL * sp->a.sms ? g : 4LL * sp->a.sms);
+  sp->ws_common = sp->a.ws_total > sp->b.ws_total ? sp->a.ws_total : sp->b.ws_total;   // same layout, pass A's stash is the larger
+  size_t o = sp->ws_common;
+  sp->off_JA = o; o += (size_t)tc::rup(n * 5 * 4, 256);
+  sp->off_JB = o; o += (size_t)tc::rup(n * 4 * 4, 256);
+  sp->off_JbA = o; o += (size_t)tc::rup(n * 5 * 4, 256);
+  sp->off_JbB = o; o += (size_t)tc::rup(n * 4 * 4, 256);
+  sp->off_ps = o; o += (size_t)tc::rup((long long)sp->blocks * 8 * 8, 256);
+  sp->ws_total = o;
+  return PDE_OK;
+}
+
 bool tc_supported(const pde_net* net, const pde_program* prog, long long n_points) {
   if (!program_ok(prog)) return false;
   const int order = pde_program_order(prog->kind);
+  if (split_shape(net, order)) {
+    SplitPlan sp;
+    return make_split_plan(net, n_points, &sp) == PDE_OK;
+  }
   tc::TcPlan p;
   return tc::make_plan(net, order, n_points, &p) == PDE_OK;
 }
 
 int tc_workspace_bytes(const pde_net* net, int order, long long n_points, size_t* bytes) {
+  if (split_shape(net, order)) {
+    SplitPlan sp;
+    int rc = make_split_plan(net, n_points, &sp);
+    if (rc) return rc;
+    *bytes = sp.ws_total;
+    return PDE_OK;
+  }
   tc::TcPlan p;
   int rc = tc::make_plan(net, order, n_points, &p);
   if (rc) return rc;
@@ -1796,6 +1895,118 @@ static int tc_run(const pde_net* net, int order, int mode, const pde_envelope* e
   return PDE_OK;
 }
 
+// The 5-D PINN step on tensor cores: pack, forward pass A (directions 0..2) and B (3..4) writing network jets, the
+// pointwise residual kernel (sums, per-point cotangents), reverse passes A and B (each recomputes its forward) whose
+// reduced gradients are added, the second reduction carrying the sums, dE and, when asked for, the exchange.
+static int tc_pinn_split(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
+                         long long n_points, const void* seed, double inv_n, void* sums, void* grad, void* energy_grad,
+                         void* workspace, size_t workspace_bytes, cudaStream_t st, const ExchangeReq* ex) {
+  using namespace tc;
+  SplitPlan sp;
+  int rc = make_split_plan(net, n_points, &sp);
+  if (rc) return rc;
+  for (int l = 0; l < sp.a.n_lin; ++l)
+    if (!net->W[l] || !net->b[l]) return PDE_ERR_INVALID;
+  if (!X || !workspace) return PDE_ERR_INVALID;
+  if (workspace_bytes < sp.ws_total) return PDE_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PDE_ERR_INVALID;
+  const bool want_grad = (grad != nullptr) || (energy_grad != nullptr);
+  unsigned char* wsb = static_cast<unsigned char*>(workspace);
+  const TcPlan& pa = sp.a;
+  float* params = reinterpret_cast<float*>(wsb);
+  unsigned char* wimg = wsb + pa.ws_params;
+  float* partial = reinterpret_cast<float*>(wsb + pa.ws_params + pa.ws_wimg);
+  double* psums_k = reinterpret_cast<double*>(wsb + pa.ws_params + pa.ws_wimg + pa.ws_partial);
+  float4* stash = reinterpret_cast<float4*>(wsb + pa.ws_params + pa.ws_wimg + pa.ws_partial + pa.ws_psums);
+  float* JA = reinterpret_cast<float*>(wsb + sp.off_JA);
+  float* JB = reinterpret_cast<float*>(wsb + sp.off_JB);
+  float* JbA = reinterpret_cast<float*>(wsb + sp.off_JbA);
+  float* JbB = reinterpret_cast<float*>(wsb + sp.off_JbB);
+  double* psums_pt = reinterpret_cast<double*>(wsb + sp.off_ps);
+
+  TcPackArgs pk;
+  memset(&pk, 0, sizeof(pk));
+  for (int l = 0; l < pa.n_lin; ++l) { pk.W[l] = static_cast<const float*>(net->W[l]); pk.b[l] = static_cast<const float*>(net->b[l]); }
+  pk.n_lin = pa.n_lin; pk.D = pa.D; pk.H = pa.H; pk.params = params; pk.wimg = wimg;
+  tc_pack_kernel<<<32, 256, 0, st>>>(pk);
+  if (cudaGetLastError() != cudaSuccess) return PDE_ERR_CUDA;
+  count_launch();
+
+  auto pass = [&](const TcPlan& p, int dir0, int mode, float* J, const float* Jbar) -> int {
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_h = p.n_h; a.act = net->activation; a.H = p.H;
+    a.params = params; a.wimg = wimg;
+    a.X = static_cast<const float*>(X); a.n = n_points; a.num_tiles = p.num_tiles;
+    a.mode = mode; a.dir0 = dir0; a.J = J; a.Jbar = Jbar;
+    a.want_grad = mode == 2;
+    a.inv_n = (float)inv_n;
+    a.partial = partial; a.psums = psums_k; a.stash = stash;
+    a.PP = p.PP; a.stash_f4 = p.stash_f4;
+    a.off_gW0 = p.off_gW0; a.off_gb0 = p.off_gb0; a.off_gW = p.off_gW; a.off_gwL = p.off_gwL; a.off_gbL = p.off_gbL;
+    if (launch_tc(p, a, st) != cudaSuccess) return PDE_ERR_CUDA;
+    count_launch();
+    return PDE_OK;
+  };
+  if ((rc = pass(sp.a, 0, 1, JA, nullptr))) return rc;
+  if ((rc = pass(sp.b, 3, 1, JB, nullptr))) return rc;
+
+  TcArgs pt;
+  memset(&pt, 0, sizeof(pt));
+  pt.X = static_cast<const float*>(X); pt.n = n_points;
+  pt.prog = prog->kind; pt.n_q = pde_program_quantities(prog->kind);
+  if (env) {
+    pt.env.kind = env->kind; pt.env.lo = (float)env->lo; pt.env.hi = (float)env->hi;
+    for (int i = 0; i < PDE_MAX_DIM; ++i) {
+      pt.env.n_nodes[i] = env->n_nodes[i];
+      for (int k = 0; k < PDE_MAX_NODES; ++k) pt.env.nodes[i][k] = (float)env->nodes[i][k];
+    }
+  }
+  pt.alpha = (float)prog->alpha; pt.beta_const = (float)prog->beta_const; pt.energy_const = (float)prog->energy_const;
+  pt.inv_n = (float)inv_n;
+  pt.f = static_cast<const float*>(prog->f); pt.beta = static_cast<const float*>(prog->beta);
+  pt.energy = static_cast<const float*>(prog->energy); pt.seed = static_cast<const float*>(seed);
+  pinn_split_kernel<<<sp.blocks, SPLIT_BLOCK, 0, st>>>(pt, JA, JB, want_grad ? JbA : nullptr, want_grad ? JbB : nullptr, psums_pt);
+  if (cudaGetLastError() != cudaSuccess) return PDE_ERR_CUDA;
+  count_launch();
+  set_last_path(1);
+
+  auto reduce = [&](const TcPlan& p, bool first, bool last) -> int {
+    ReduceArgs<float> r;
+    memset(&r, 0, sizeof(r));
+    r.partial = partial; r.psums = psums_pt; r.psum_grid = sp.blocks; r.PP = p.PP; r.grid = p.grid; r.n_lin = p.n_lin; r.D = p.D; r.H = p.H;
+    r.Hp = HP; r.n_q = pt.n_q;
+    r.off_gW0 = p.off_gW0; r.off_gb0 = p.off_gb0; r.off_gW = p.off_gW; r.off_gwL = p.off_gwL; r.off_gbL = p.off_gbL;
+    r.n_params = p.n_params;
+    r.grad = static_cast<float*>(grad);
+    r.accumulate = first ? 0 : 1;
+    r.sums = last ? static_cast<float*>(sums) : nullptr;
+    r.energy_grad = last ? static_cast<float*>(energy_grad) : nullptr;
+    if (ex && last) {
+      if (!r.grad || !r.sums || !r.energy_grad) return PDE_ERR_INVALID;
+      int rc2 = comm_fill_args(ex->peers, PDE_F32, p.n_params + 1 + pt.n_q, ex->slot_elems, ex->seq, &r.comm);
+      if (rc2) return rc2;
+      r.have_comm = 1;
+    }
+    if (launch_reduce<float>(st, r) != cudaSuccess) return PDE_ERR_CUDA;
+    return PDE_OK;
+  };
+  if (!want_grad || !grad) {
+    // value only (or dE only): one reduction for the sums; a zero-sized gradient pass is not needed
+    ReduceArgs<float> r;
+    memset(&r, 0, sizeof(r));
+    r.partial = partial; r.psums = psums_pt; r.psum_grid = sp.blocks; r.PP = pa.PP; r.grid = 0; r.n_lin = pa.n_lin; r.D = pa.D; r.H = pa.H;
+    r.Hp = HP; r.n_q = pt.n_q; r.n_params = pa.n_params;
+    r.sums = static_cast<float*>(sums); r.energy_grad = static_cast<float*>(energy_grad);
+    if (launch_reduce<float>(st, r) != cudaSuccess) return PDE_ERR_CUDA;
+    return PDE_OK;
+  }
+  if ((rc = pass(sp.a, 0, 2, nullptr, JbA))) return rc;
+  if ((rc = reduce(sp.a, true, false))) return rc;
+  if ((rc = pass(sp.b, 3, 2, nullptr, JbB))) return rc;
+  return reduce(sp.b, false, true);
+}
+
 int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde_program* prog, const void* X,
                           long long n_points, const void* seed, double inv_n, void* sums, void* grad,
                           void* energy_grad, void* workspace, size_t workspace_bytes, cudaStream_t st, const ExchangeReq* ex) {
@@ -1803,6 +2014,10 @@ int tc_residual_loss_grad(const pde_net* net, const pde_envelope* env, const pde
   const int order = pde_program_order(prog->kind);
   if (order < 0) return PDE_ERR_INVALID;
   if (!program_ok(prog)) return PDE_ERR_UNSUPPORTED;
+  if (split_shape(net, order)) {
+    if (prog->kind != PDE_PROG_PINN) return PDE_ERR_UNSUPPORTED;
+    return tc_pinn_split(net, env, prog, X, n_points, seed, inv_n, sums, grad, energy_grad, workspace, workspace_bytes, st, ex);
+  }
   return tc_run(net, order, 0, env, prog, X, n_points, seed, inv_n, nullptr, nullptr, sums, grad, energy_grad, workspace,
                 workspace_bytes, st, ex);
 }

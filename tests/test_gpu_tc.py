@@ -51,7 +51,8 @@ def _grads(lin):
     return [l.weight.grad.double().cpu().numpy() for l in lin], [l.bias.grad.double().cpu().numpy() for l in lin]
 
 
-GOLDEN = [("poisson_pinn_d1_w64_fbc", "pinn", "FBC"), ("poisson_pinn_d3_w64_fbc", "pinn", "FBC"),
+GOLDEN = [("poisson_pinn_d5_w16_fbc", "pinn", "FBC"),      # 7 jet channels: the dimension-split path (two passes + pointwise kernel)
+          ("poisson_pinn_d1_w64_fbc", "pinn", "FBC"), ("poisson_pinn_d3_w64_fbc", "pinn", "FBC"),
           ("poisson_drm_d5_w64_rb", "drm", "RB"), ("poisson_pinn_d2_w16_fbc", "pinn", "FBC"),
           ("poisson_pinn_d3_w16_rb", "pinn", "RB"), ("poisson_pinn_d4_w12_fbc", "pinn", "FBC"),
           ("poisson_drm_d1_w16_fbc", "drm", "FBC"), ("poisson_drm_d2_w16_fbc", "drm", "FBC"),
@@ -188,7 +189,7 @@ def test_tc_chunk_linearity_full_size_and_determinism():
 
 def test_path_selection():
     """Default routing: tensor-core kernel for the shapes it covers above 4096 points, generic kernel
-    otherwise (fp64, wide nets, 7 jet channels); pde_set_kernel_path overrides."""
+    otherwise (fp64, wide nets); pde_set_kernel_path overrides."""
     import pde_b200 as pb
     with pb.ops.kernel_path("auto"):
         _path_selection(pb)
@@ -207,8 +208,8 @@ def _path_selection(pb):
     assert pb.ops.last_kernel_path() == "simt_fma"
     m5 = pb.poisson.SolutionNet(5, 64, 5, "FBC").cuda()
     X5 = torch.rand(8192, 5, device="cuda") * 2
-    pb.poisson.pinn_residual_loss(m5, X5, f, 2.0)          # 1 + 5 + 1 = 7 channels: generic kernel
-    assert pb.ops.last_kernel_path() == "simt_fma"
+    pb.poisson.pinn_residual_loss(m5, X5, f, 2.0)          # 1 + 5 + 1 = 7 channels: two dimension-split tensor-core passes
+    assert pb.ops.last_kernel_path() == "tcgen05"
     pb.poisson.drm_energy_loss(m5, X5, f, 2.0)             # 1 + 5 = 6 channels: tensor cores
     assert pb.ops.last_kernel_path() == "tcgen05"
     from pde_b200 import _lib as L
@@ -344,3 +345,54 @@ def test_tc_adjoint_scale_follows_the_residual():
         assert math.isfinite(l32.item())
         assert abs(l32.item() - l64.item()) <= TOL * abs(l64.item())
         assert_grads_close(_grads(lin32), _grads(lin64), TOL, f"ramp {ramp}")
+
+
+@pytest.mark.parametrize("act,bc,w,depth,N", [("sin", "FBC", 64, 5, 4099), ("sin", "RB", 40, 4, 777), ("tanh", "FBC", 64, 3, 1500)])
+def test_tc_pinn_5d_split_vs_numpy_oracle(act, bc, w, depth, N):
+    """5-D PINN (7 jet channels) on the tensor-core kernel: forward passes over directions 0..2 and 3..4, the pointwise
+    residual kernel, two reverse passes whose gradients add up — loss and gradient vs oracle/jets_numpy (float64)."""
+    import pde_b200 as pb
+    from pde_b200 import _lib as L
+    from pde_b200.ops import EnvelopeSpec, ProgramSpec, residual_means
+    from oracle import jets_numpy as O
+    rng = np.random.default_rng(77)
+    Ws, bs = _rand_net(rng, 5, w, depth)
+    X = rng.uniform(0.05, 1.95, (N, 5)).astype(np.float32).astype(np.float64)
+    f = rng.normal(size=(N, 1)).astype(np.float32).astype(np.float64)
+    A = O.SIN if act == "sin" else O.TANH
+    want, gWs, gbs = O.poisson_pinn_loss(Ws, bs, X, f, 2.0, bc, act=A)
+    net, lin = _seq(Ws, bs, act)
+    env = EnvelopeSpec(L.ENV_POLY, 0.0, 2.0) if bc == "FBC" else pb.ops.NO_ENVELOPE
+    loss = residual_means(net, torch.tensor(X, dtype=torch.float32, device="cuda"), ProgramSpec(L.PROG_PINN, -1.0), env,
+                          f=torch.tensor(f, dtype=torch.float32, device="cuda"))[0]
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    loss.backward()
+    assert abs(loss.item() - want) <= TOL * abs(want), (loss.item(), want)
+    assert_grads_close(_grads(lin), (gWs, gbs), TOL, f"5-D pinn {act} {bc}")
+    with torch.no_grad():       # value only: no reverse passes
+        l0 = residual_means(net, torch.tensor(X, dtype=torch.float32, device="cuda"), ProgramSpec(L.PROG_PINN, -1.0), env,
+                            f=torch.tensor(f, dtype=torch.float32, device="cuda"))[0]
+    assert abs(l0.item() - want) <= TOL * abs(want)
+
+
+def test_tc_pinn_5d_split_large_batch_against_fp64_generic_kernel():
+    """2^18 points, default-width network: the split tensor-core path vs the float64 generic kernel."""
+    import pde_b200 as pb
+    from pde_b200 import _lib as L
+    from pde_b200.ops import EnvelopeSpec, ProgramSpec, residual_means
+    rng = np.random.default_rng(5)
+    Ws, bs = _rand_net(rng, 5, 64, 5)
+    n32, lin32 = _seq(Ws, bs, "sin")
+    n64, lin64 = _seq(Ws, bs, "sin", torch.float64)
+    N = 1 << 18
+    X32 = torch.rand(N, 5, device="cuda") * 1.9 + 0.05
+    f32 = torch.randn(N, device="cuda")
+    espec = EnvelopeSpec(L.ENV_POLY, 0.0, 2.0)
+    l32 = residual_means(n32, X32, ProgramSpec(L.PROG_PINN, -1.0), espec, f=f32)[0]
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    l32.backward()
+    with pb.ops.kernel_path("simt"):
+        l64 = residual_means(n64, X32.double(), ProgramSpec(L.PROG_PINN, -1.0), espec, f=f32.double())[0]
+        l64.backward()
+    assert abs(l32.item() - l64.item()) <= TOL * abs(l64.item())
+    assert_grads_close(_grads(lin32), _grads(lin64), TOL, "5-D, 2^18 points")

@@ -32,5 +32,6 @@ if __name__ == "__main__":
     run(3, "pinn", "FBC", 1 << 20)
     run(3, "pinn", "FBC", 1 << 22, iters=3)
     run(5, "drm", "RB", 1 << 20)
+    run(5, "pinn", "FBC", 1 << 20)          # 7 jet channels: dimension-split tensor-core passes
     run(1, "pinn", "FBC", 20000)
     run(3, "pinn", "FBC", 1 << 16, dtype=torch.float64, iters=2)
