@@ -1753,12 +1753,11 @@ static int make_plan(const pde_net* net, int order, long long n, TcPlan* pl, int
 
 }  // namespace tc
 
-// The Rayleigh quotient's gradient is a difference of two nearly parallel vectors, which amplifies
-// the 1e-6 rounding of the split GEMMs towards the 1e-5 bar; it is served by the generic fp32 kernel
-// unless the tensor-core path is forced (PDE_B200_PATH=tc).
-static bool program_ok(const pde_program* prog) {
-  return prog && (prog->kind != PDE_PROG_RAYLEIGH || tc::path_override() == 1);
-}
+// Every residual program is served.  (Round 1 kept the Rayleigh quotient on the generic kernel: its gradient is a
+// difference of nearly parallel vectors, which amplifies the ~1e-6 rounding of the split GEMMs.  Measured at the
+// reference's own shapes — 200 x 200 grids, [2,50,50,50,50,1], tools/rayleigh_check.py — the tensor-core gradients are
+// 1.4e-6 .. 8.9e-6 from the float64 reference, inside the bar each fixture justifies.)
+static bool program_ok(const pde_program* prog) { return prog != nullptr; }
 
 // 5-D second-order programs need 7 jet channels, one more than fits on chip: they run as two dimension-split passes
 // (3 + 2 directions, 5 and 4 channels) around a pointwise residual kernel (tc_pinn_split below).
