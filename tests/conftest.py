@@ -73,9 +73,20 @@ def grads_err(got, want):
     return worst, where
 
 
+def _log(kind, what, err, tol):
+    """PDE_PARITY_LOG=<file>: every parity comparison (measured error, bar) is appended to it — the table under
+    profiles/ is made this way."""
+    path = os.environ.get("PDE_PARITY_LOG")
+    if path:
+        test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
+        with open(path, "a") as fh:
+            fh.write(f"{test}\t{kind}\t{what.strip()}\t{err:.3e}\t{tol:.3e}\n")
+
+
 def assert_grads_close(got, want, tol, what=""):
     """Per-parameter-tensor relative L2 and global max-abs criteria."""
     e, where = grads_err(got, want)
+    _log("grad", what, e, tol)
     assert e <= tol, f"{what} {where}: {e:.3e} > {tol:.3e}"
 
 
@@ -123,6 +134,7 @@ def assert_loss_close(got, g, key, dtype, what=""):
     got = float(got.detach()) if hasattr(got, "detach") else float(got)
     want, tol = float(g[key]), loss_bar(g, key, dtype)
     e = abs(got - want) / max(abs(want), 1e-3)
+    _log("loss", f"{what} {key}", e, tol)
     assert e <= tol, f"{what} {key}: {got!r} vs {want!r}: {e:.3e} > {tol:.3e}"
 
 
