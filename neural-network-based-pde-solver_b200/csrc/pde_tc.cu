@@ -558,13 +558,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       uint32_t ph_chunk = 0, ph_own = 0, ph_wt = 0;
       int reg = 0;   // region the next D-producing GEMM writes
       int cur_w = 1;   // layer whose W sits in the single buffer (non-resident W)
-      // make W_l the resident tile pair: drain my MMAs (they may read the buffer), then one bulk copy
-      auto need_w = [&](int l) {
-        if (WRES || cur_w == l) return;
-        if (elect_one()) mma_commit(bar_own);
-        __syncwarp();
-        mbar_wait(bar_own, ph_own);
-        ph_own ^= 1;
+      // Non-resident W (6 channels): one tile-pair buffer, refilled with a bulk copy.  need_w(l) makes W_l current:
+      // drain my MMAs (they may read the buffer), copy, wait.  In the reverse sweep the copy of W_{l-1} is started as
+      // soon as dgrad_l has completed — wgrad_l, which runs for another ~2.6 k cycles, does not read W — so only its
+      // arrival is waited for when layer l-1 starts.
+      bool w_loading = false;
+      auto start_w_load = [&](int l) {
         if (elect_one()) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_wt)), "r"(2 * TILE_BYTES) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWT),
@@ -572,9 +571,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
                        : "memory");
         }
         __syncwarp();
-        mbar_wait(bar_wt, ph_wt);
-        ph_wt ^= 1;
         cur_w = l;
+        w_loading = true;
+      };
+      auto need_w = [&](int l) {
+        if (WRES) return;
+        if (cur_w != l) {
+          if (elect_one()) mma_commit(bar_own);
+          __syncwarp();
+          mbar_wait(bar_own, ph_own);
+          ph_own ^= 1;
+          start_w_load(l);
+        }
+        if (w_loading) {
+          mbar_wait(bar_wt, ph_wt);
+          ph_wt ^= 1;
+          w_loading = false;
+        }
       };
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         // ---- forward GEMMs of layers 1..n_h-1, K step j as soon as chunk j of A_{l-1} is there
@@ -628,7 +641,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
             __syncwarp();
           }
-          if (elect_one()) mma_commit(bar_d);
+          if (elect_one()) {
+            mma_commit(bar_d);
+            if (!WRES && l > 1) mma_commit(bar_own);   // "dgrad_l has completed": the W buffer may be refilled
+          }
           __syncwarp();
           ph_chunk ^= 1;
           reg ^= 1;
@@ -663,6 +679,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             mma_commit(bar_w);
           }
           __syncwarp();
+          if (!WRES && l > 1) {
+            mbar_wait(bar_own, ph_own);
+            ph_own ^= 1;
+            start_w_load(l - 1);   // under wgrad_l
+          }
         }
         // ---- first layer: [gW0 | gb0] += Zb_{0,0}^T [x | 1] + sum_i Zb_{0,i}^T e_i
         {
