@@ -478,6 +478,11 @@ def main():
     dev = torch.device("cuda", local)
     group = None
     exchange = "none (one rank)"
+    # stdout carries the one JSON line only: whatever libraries print while the job runs (NCCL's version banner goes to
+    # stdout whatever NCCL_DEBUG_FILE says) is sent to stderr; file descriptor 1 is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
@@ -657,6 +662,8 @@ def main():
                 out["torch_eager_gpu_baseline"] = {"value": None, "error": type(exc).__name__}
             if not args.no_extra_configs:
                 out["extra_configs"] = extra_configs(dev, peak)
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
