@@ -179,6 +179,16 @@ int pde_wan_pointwise(const pde_wan* wan, const void* X, int64_t n_points, const
                       const void* Jv, const void* seed, double inv_n, void* sums, void* Jbar_u,
                       void* Jbar_v, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The scalar end of the WAN losses in one launch: out = (loss_pde, loss_v, loss_norm, total) of the four means of
+ * pde_wan_pointwise and jac = d out_i / d mean_j (4 x 4, row major), both device arrays of the given dtype.
+ *   kind 0: loss_pde = m0^2 / (m1 + eps_pde)                          Poisson_ND.py:118-122, IPW_1D_WAN.py:108-110, QHO_2D.py:218-219
+ *   kind 1: loss_pde = (vol m0 / (vol m1 + eps_pde))^2               KH_1D.py:263-267
+ *   loss_v = -log(loss_pde + eps_log) + reg m3;  loss_norm = (vol m2 - 1)^2;  total = w_pde loss_pde + w_norm loss_norm
+ *   consts (host, 6 doubles): eps_pde, eps_log, vol, reg, w_pde, w_norm.
+ * Replaces: the ~25 zero-dimensional tensor operations (and their autograd nodes) each reference WAN_loss ends with. */
+int pde_wan_scalars(int32_t dtype, int32_t kind, const void* means, const double* consts, void* out, void* jac,
+                    void* stream);
+
 /* ---- the device-side pieces of an epoch around the loss step (all single launches, graph capturable) ---- */
 
 /* Collocation-point sampling with the manufactured solution / right-hand side in the same pass.

@@ -20,7 +20,7 @@ EXPORTS = [
     "pde_residual_loss_grad", "pde_wan_pointwise", "pde_query_path", "pde_sample_points_rhs", "pde_adam_step",
     "pde_keep_best", "pde_peer_bytes", "pde_peer_alloc", "pde_peer_open", "pde_peer_close", "pde_peer_free",
     "pde_allreduce_oneshot", "pde_query_jets_path", "pde_set_kernel_path", "pde_kernel_path", "pde_last_kernel_path",
-    "pde_launch_count", "pde_set_exchange_timeout", "pde_exchange_errors", "pde_residual_loss_grad_exchange",
+    "pde_launch_count", "pde_set_exchange_timeout", "pde_exchange_errors", "pde_residual_loss_grad_exchange", "pde_wan_scalars",
 ]
 MAX_PEERS = 8
 
@@ -95,6 +95,7 @@ def load():
                                            vp, vp, vp, vp, sz, vp]
     lib.pde_residual_loss_grad_exchange.argtypes = [C.POINTER(Net), C.POINTER(Envelope), C.POINTER(Program), vp, i64, vp, dbl,
                                                     vp, vp, sz, C.POINTER(Peers), i64, vp, vp]
+    lib.pde_wan_scalars.argtypes = [i32, i32, vp, C.POINTER(dbl), vp, vp, vp]
     lib.pde_query_path.argtypes = [C.POINTER(Net), C.POINTER(Program), i64]
     lib.pde_wan_pointwise.argtypes = [C.POINTER(Wan), vp, i64, vp, vp, vp, dbl, vp, vp, vp, vp, sz, vp]
     lib.pde_sample_points_rhs.argtypes = [i32, i32, i64, dbl, dbl, C.c_uint64, C.c_uint64, vp, C.POINTER(dbl), dbl, vp, vp,

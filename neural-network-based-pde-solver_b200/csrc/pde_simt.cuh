@@ -699,6 +699,7 @@ __global__ void reduce_kernel(const ReduceArgs<T> a) {
       const int col = (k < a.n_q) ? k : 4;
       double v = 0.0;
       const int pg = a.psum_grid > 0 ? a.psum_grid : a.grid;
+#pragma unroll 8
       for (int g = 0; g < pg; ++g) v += a.psums[(long long)g * 8 + col];
       T r = (T)v;
       if (a.have_comm) r = comm::exchange_element<T>(a.comm, (k < a.n_q) ? a.n_params + 1 + k : a.n_params, r, call);
@@ -730,7 +731,9 @@ __global__ void reduce_kernel(const ReduceArgs<T> a) {
         }
       }
     }
+    // fixed order g = 0, 1, ...; unrolled so that eight of the (independent, L2-latency) loads are in flight
     double v = 0.0;
+#pragma unroll 8
     for (int g = 0; g < a.grid; ++g) v += (double)a.partial[(long long)g * a.PP + src];
     T r = (T)v;
     if (a.accumulate) r += *dst;

@@ -183,9 +183,64 @@ int grid_for(long long n, int block) {
   return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
 }
 
+// The scalar end of the WAN losses: (loss_pde, loss_v, loss_norm, total) of the four means and the 4 x 4 Jacobian
+// d out_i / d mean_j, one thread.  The reference evaluates these with ~25 separate 0-d tensor operations per call
+// (Poisson_ND.py:118-127, IPW_1D_WAN.py:108-114, QHO_2D.py:218-224, KH_1D.py:263-268), which at 1000 points costs as
+// much as the network sweeps.
+struct WanScalarArgs {
+  int kind;
+  double eps_pde, eps_log, vol, reg, w_pde, w_norm;
+  const void* m;
+  void* out;
+  void* jac;
+};
+template <typename T>
+__global__ void wan_scalars_kernel(const WanScalarArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const T* m = static_cast<const T*>(a.m);
+  T* out = static_cast<T*>(a.out);
+  T* J = static_cast<T*>(a.jac);
+  const T m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+  const T e1 = (T)a.eps_pde, e2 = (T)a.eps_log, vol = (T)a.vol, reg = (T)a.reg, wp = (T)a.w_pde, wn = (T)a.w_norm;
+  T pde, d0, d1;
+  if (a.kind == 0) {          // weak^2 / (norm_phi + eps)
+    const T den = m1 + e1;
+    pde = m0 * m0 / den;
+    d0 = T(2) * m0 / den;
+    d1 = -(m0 * m0) / (den * den);
+  } else {                    // KH: (vol * weak / (vol * norm_phi + eps))^2
+    const T I = vol * m0, den = vol * m1 + e1, r = I / den;
+    pde = r * r;
+    d0 = T(2) * r * vol / den;
+    d1 = -T(2) * r * I * vol / (den * den);
+  }
+  const T k = -T(1) / (pde + e2);
+  const T lv = -log(pde + e2) + reg * m3;
+  const T nv = vol * m2 - T(1);
+  for (int i = 0; i < 16; ++i) J[i] = T(0);
+  out[0] = pde;             J[0] = d0;          J[1] = d1;
+  out[1] = lv;              J[4] = k * d0;      J[5] = k * d1;      J[7] = reg;
+  out[2] = nv * nv;         J[10] = T(2) * nv * vol;
+  out[3] = wp * pde + wn * nv * nv;
+  J[12] = wp * d0;          J[13] = wp * d1;    J[14] = wn * T(2) * nv * vol;
+}
+
 }  // namespace
 
 extern "C" {
+
+int pde_wan_scalars(int32_t dtype, int32_t kind, const void* means, const double* consts, void* out, void* jac, void* stream) {
+  if ((dtype != PDE_F32 && dtype != PDE_F64) || kind < 0 || kind > 1 || !means || !consts || !out || !jac) return PDE_ERR_INVALID;
+  WanScalarArgs a;
+  a.kind = kind;
+  a.eps_pde = consts[0]; a.eps_log = consts[1]; a.vol = consts[2]; a.reg = consts[3]; a.w_pde = consts[4]; a.w_norm = consts[5];
+  a.m = means; a.out = out; a.jac = jac;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == PDE_F32) wan_scalars_kernel<float><<<1, 32, 0, st>>>(a);
+  else wan_scalars_kernel<double><<<1, 32, 0, st>>>(a);
+  pde::count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? PDE_OK : PDE_ERR_CUDA;
+}
 
 int pde_sample_points_rhs(int32_t dtype, int32_t dim, int64_t n_points, double lo, double hi, uint64_t seed,
                           uint64_t offset, const void* offset_add, const double* k, double period, const void* X_in,

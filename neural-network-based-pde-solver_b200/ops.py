@@ -585,6 +585,42 @@ def wan_means(u_model, v_model, X, spec: WanSpec, env_u=NO_ENVELOPE, env_v=NO_EN
     return means
 
 
+class _WanScalars(torch.autograd.Function):
+    """(loss_pde, loss_v, loss_norm, total) of the four WAN means in one launch (pde_wan_scalars); backward = J^T g."""
+
+    @staticmethod
+    def forward(ctx, means, kind, consts):
+        lib = L.load()
+        dev, dt = means.device, means.dtype
+        m = means.detach().contiguous()
+        out = torch.empty(4, dtype=dt, device=dev)
+        jac = torch.empty(4, 4, dtype=dt, device=dev)
+        carr = (C.c_double * 6)(*[float(c) for c in consts])
+        with torch.cuda.device(dev):
+            L.check(lib.pde_wan_scalars(L.F64 if dt == torch.float64 else L.F32, int(kind), m.data_ptr(), carr, out.data_ptr(),
+                                        jac.data_ptr(), _stream(dev)), "pde_wan_scalars")
+        ctx.save_for_backward(jac)
+        ctx.set_materialize_grads(False)
+        return out[0], out[1], out[2], out[3]
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        (jac,) = ctx.saved_tensors
+        gm = None
+        for k, g in enumerate(gouts):
+            if g is not None:
+                t = jac[k] * g
+                gm = t if gm is None else gm + t
+        return gm, None, None
+
+
+def wan_scalar_losses(means, *, kind=0, eps_pde=1e-8, eps_log=1e-8, vol=1.0, reg=0.0, w_pde=1.0, w_norm=1.0):
+    """(loss_pde, loss_v, loss_norm, total) from the means of ``wan_means`` — the scalar end of every reference
+    WAN_loss (Poisson_ND.py:118-127, IPW_1D_WAN.py:108-114, QHO_2D.py:218-224, KH_1D.py:263-268) as one launch
+    instead of ~25 zero-dimensional tensor operations."""
+    return _WanScalars.apply(means, kind, (eps_pde, eps_log, vol, reg, w_pde, w_norm))
+
+
 def _check_jets(J, X):
     if J.shape != (X.shape[0], 1 + X.shape[1]) or J.dtype != X.dtype or J.device != X.device:
         raise ValueError("frozen jets must be the (N, 1+d) order-1 jets of the same points")

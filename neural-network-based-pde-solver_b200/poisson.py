@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, mlp_jets, residual_means, wan_means)
+from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, mlp_jets, residual_means, wan_means, wan_scalar_losses)
 
 
 class Sin(nn.Module):
@@ -107,10 +107,8 @@ def wan_losses(u_model, v_model, X, f_vals, L, eps=1e-8, v_reg_weight=0.0, *, gr
     assert X.requires_grad, "X must require_grad=True"
     m = wan_means(u_model, v_model, X, WanSpec(alpha=1.0, w_lo=0.0, w_hi=float(L)), env_u=_envelope(u_model, L),
                   env_v=NO_ENVELOPE, f=f_vals, group=group, n_global=n_global, u_jets=u_jets, v_jets=v_jets)
-    weak, phi_norm, v_reg = m[0], m[1], m[3]
-    loss_pde_u = weak ** 2 / (phi_norm + eps)
-    loss_v = -torch.log(loss_pde_u + eps) + v_reg_weight * v_reg
-    return loss_pde_u, loss_v, weak.detach(), phi_norm.detach()
+    loss_pde_u, loss_v, _, _ = wan_scalar_losses(m, kind=0, eps_pde=eps, eps_log=eps, reg=v_reg_weight)
+    return loss_pde_u, loss_v, m[0].detach(), m[1].detach()
 
 
 def boundary_loss_dirichlet(model, L, N_b_per_face, dim, device, *, group=None):

@@ -3,7 +3,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ..ops import WanSpec, wan_means
+from ..ops import WanSpec, wan_means, wan_scalar_losses
 from ._common import NO_ENVELOPE, mlp, poly_envelope
 
 
@@ -38,8 +38,5 @@ def WAN_loss(u_model, v_model, x, n, L, weight_pde=1.0, weight_norm=1.0, *, u_je
     -1/2 u'' = E_n u against phi = w v, normalised by mean(phi^2), plus (L mean(u^2) - 1)^2."""
     m = wan_means(u_model, v_model, x, WanSpec(alpha=0.5, energy_const=Exact_energy(n, L), w_lo=0.0, w_hi=float(L)),
                   env_u=_envelope(u_model), env_v=_envelope(v_model), u_jets=u_jets, v_jets=v_jets)
-    loss_pde = m[0] ** 2 / (m[1] + 1e-8)
-    loss_norm = (L * m[2] - 1.0) ** 2
-    total_loss = weight_pde * loss_pde + weight_norm * loss_norm
-    loss_v = -torch.log(loss_pde + 1e-8)
+    loss_pde, loss_v, loss_norm, total_loss = wan_scalar_losses(m, kind=0, vol=L, w_pde=weight_pde, w_norm=weight_norm)
     return total_loss, loss_v, loss_pde, loss_norm

@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import NO_ENVELOPE, ProgramSpec, WanSpec, residual_means, wan_means
+from ..ops import NO_ENVELOPE, ProgramSpec, WanSpec, residual_means, wan_means, wan_scalar_losses
 from ._common import Sin, mlp, window_envelope
 
 
@@ -115,6 +115,5 @@ def wan_loss(model, v_model, x, alpha, V0, L, use_avg=True, n_theta=500, *, u_je
     m = wan_means(model, v_model, x, WanSpec(alpha=0.5, w_lo=-float(L), w_hi=float(L), eps_den=1e-10),
                   env_u=_envelope(model, L), env_v=_envelope(v_model, L), beta=Vx, energy=model.energy,
                   u_jets=u_jets, v_jets=v_jets)
-    I_full = (2 * L) * m[0]
-    norm_phi = (2 * L) * m[1] + 1e-12
-    return (I_full / norm_phi) ** 2, ((2 * L) * m[2] - 1.0) ** 2
+    pde_loss, _, norm_u, _ = wan_scalar_losses(m, kind=1, eps_pde=1e-12, vol=2 * L)
+    return pde_loss, norm_u

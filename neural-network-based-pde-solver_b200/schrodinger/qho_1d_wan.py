@@ -3,7 +3,7 @@ network for the 1-D oscillator, trainable energy)."""
 import torch
 import torch.nn as nn
 
-from ..ops import WanSpec, wan_means
+from ..ops import WanSpec, wan_means, wan_scalar_losses
 from ._common import NO_ENVELOPE, mlp, window_envelope
 from .qho_1d_pinn_drm import Energy, Exact_solution, Potential, phys_hermite  # noqa: F401  (same helpers, :25-53)
 
@@ -39,8 +39,5 @@ def WAN_loss(u_model, v_model, x, n, L, weight_pde=1.0, weight_norm=1.0, *, u_je
     V = Potential(x.detach())
     m = wan_means(u_model, v_model, x, WanSpec(alpha=0.5, w_lo=-float(L), w_hi=float(L)),
                   env_u=_envelope(u_model), env_v=_envelope(v_model), beta=V, energy=u_model.energies, u_jets=u_jets, v_jets=v_jets)
-    loss_pde = m[0] ** 2 / (m[1] + 1e-8)
-    loss_norm = (2 * L * m[2] - 1.0) ** 2
-    total_loss = weight_pde * loss_pde + weight_norm * loss_norm
-    loss_v = -torch.log(loss_pde + 1e-8)
+    loss_pde, loss_v, loss_norm, total_loss = wan_scalar_losses(m, kind=0, vol=2 * L, w_pde=weight_pde, w_norm=weight_norm)
     return total_loss, loss_v, loss_pde, loss_norm

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import ProgramSpec, WanSpec, residual_means, wan_means
+from ..ops import ProgramSpec, WanSpec, residual_means, wan_means, wan_scalar_losses
 from ._common import Sin, mlp, window_envelope
 
 OMEGA = math.sqrt(2)
@@ -91,8 +91,5 @@ def WAN_loss(u_model, v_model, x, y, nx, ny, L, weight_pde=1.0, weight_norm=1.0,
     m = wan_means(u_model, v_model, X, WanSpec(alpha=0.5, energy_const=Exact_energy(nx, ny, L), w_lo=-float(L), w_hi=float(L),
                                                eps_den=1e-10),
                   env_u=_envelope(u_model, L), env_v=_envelope(v_model, L), beta=V, u_jets=u_jets, v_jets=v_jets)
-    loss_pde = m[0] ** 2 / (m[1] + 1e-8)
-    loss_norm = (4 * L * L * m[2] - 1.0) ** 2
-    total_loss = weight_pde * loss_pde + weight_norm * loss_norm
-    loss_v = -torch.log(loss_pde + 1e-8)
+    loss_pde, loss_v, loss_norm, total_loss = wan_scalar_losses(m, kind=0, vol=4 * L * L, w_pde=weight_pde, w_norm=weight_norm)
     return total_loss, loss_v, loss_pde, loss_norm
