@@ -81,6 +81,16 @@ class EnvelopeSpec:
     nodes: Sequence[Sequence[float]] = field(default_factory=list)
 
     def to_c(self) -> L.Envelope:
+        # the ctypes struct is rebuilt only when the description changed (40 element assignments otherwise, per call)
+        key = (int(self.kind), float(self.lo), float(self.hi), tuple(tuple(float(v) for v in ns) for ns in self.nodes))
+        cached = getattr(self, "_c_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        e = self._build_c()
+        object.__setattr__(self, "_c_cache", (key, e))
+        return e
+
+    def _build_c(self) -> L.Envelope:
         e = L.Envelope()
         e.kind, e.lo, e.hi = int(self.kind), float(self.lo), float(self.hi)
         for i, ns in enumerate(self.nodes):
@@ -192,10 +202,19 @@ def _workspace(device, nbytes):
     return buf
 
 
+_WS_NEED = {}
+
+
 def _ws_for(cnet, order, n, device):
-    need = C.c_size_t(0)
-    L.check(L.load().pde_workspace_bytes(C.byref(cnet), order, n, C.byref(need)), "pde_workspace_bytes")
-    return _workspace(device, need.value)
+    # the size depends on the network geometry, order, point count and device only (pde_workspace_bytes is pure)
+    key = (cnet.dtype, cnet.dim, cnet.n_linear, cnet.activation, tuple(cnet.widths[:cnet.n_linear + 1]), order, n,
+           device.index if device.index is not None else torch.cuda.current_device(), L.load().pde_kernel_path())
+    need = _WS_NEED.get(key)
+    if need is None:
+        val = C.c_size_t(0)
+        L.check(L.load().pde_workspace_bytes(C.byref(cnet), order, n, C.byref(val)), "pde_workspace_bytes")
+        need = _WS_NEED[key] = val.value
+    return _workspace(device, need)
 
 
 def _stream(device):
