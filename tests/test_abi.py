@@ -74,3 +74,28 @@ def test_no_cpu_fallback():
     src = open(os.path.join(ROOT, "neural-network-based-pde-solver_b200", "ops.py")).read()
     src += open(os.path.join(ROOT, "neural-network-based-pde-solver_b200", "poisson.py")).read()
     assert "oracle" not in src
+
+
+def test_host_side_settings():
+    """Process-wide settings and counters that need no device: kernel-family override, exchange timeout, launch counter."""
+    lib = pb.load_library()
+    old = lib.pde_kernel_path()
+    try:
+        for v in (-1, 0, 1):
+            assert lib.pde_set_kernel_path(v) == 0 and lib.pde_kernel_path() == v
+        assert lib.pde_set_kernel_path(2) == -1 and lib.pde_set_kernel_path(-3) == -1
+        with pb.ops.kernel_path("simt"):
+            assert lib.pde_kernel_path() == 0
+            with pb.ops.kernel_path("tc"):
+                assert lib.pde_kernel_path() == 1
+            assert lib.pde_kernel_path() == 0
+    finally:
+        lib.pde_set_kernel_path(old)
+    assert lib.pde_set_exchange_timeout(600.0) == 0 and lib.pde_set_exchange_timeout(0.0) == 0
+    assert lib.pde_set_exchange_timeout(-1.0) == -1 and lib.pde_set_exchange_timeout(float("nan")) == -1
+    lib.pde_set_exchange_timeout(600.0)
+    assert lib.pde_last_kernel_path() in (-1, 0, 1)
+    assert isinstance(pb.ops.launch_count(), int) and pb.ops.launch_count() >= 0
+    # invalid arguments are refused before anything is enqueued
+    assert lib.pde_wan_scalars(L.F32, 5, None, None, None, None, None) == -1
+    assert lib.pde_residual_loss_grad_exchange(None, None, None, None, 0, None, 1.0, None, None, 0, None, 0, None, None) == -1

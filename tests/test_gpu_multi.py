@@ -124,6 +124,29 @@ def _w_loss_api(rank, world):
         assert float((p.grad - w).abs().max()) <= 1e-5 * float(w.abs().max())
 
 
+def _w_loss_api_5d(rank, world):
+    """5-D PINN (two dimension-split tensor-core passes): the exchange rides the second reduction only."""
+    import pde_b200 as pb
+    L, n_loc = 2.0, 4096
+    torch.manual_seed(5)
+    m = pb.poisson.SolutionNet(5, 64, 4, "FBC").cuda()
+    X = torch.rand(n_loc * world, 5, device="cuda") * L
+    f = pb.poisson.rhs_f_for_u_sin(X, L, [1] * 5)
+    big = pb.poisson.pinn_residual_loss(m, X, f, L); big.backward()
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    want = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    pb.ops.use_nvlink_exchange(None, 1 << 15, torch.float32)
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    part = pb.poisson.pinn_residual_loss(m, X[sl], f[sl], L, group=torch.distributed.group.WORLD)   # n_global defaults to n x world
+    part.backward()
+    assert pb.ops.last_kernel_path() == "tcgen05"
+    assert abs(float(part) - float(big)) <= 2e-6 * abs(float(big))
+    for p, w in zip(m.parameters(), want):
+        assert float((p.grad - w).abs().max()) <= 1e-5 * float(w.abs().max())
+    pb.ops._EXCHANGE[(torch.distributed.group.WORLD, torch.float32)].check()
+
+
 def test_nvlink_allreduce_matches_rank_ordered_sum():
     _need(2)
     _run(_w_allreduce, min(torch.cuda.device_count(), 8))
@@ -138,3 +161,8 @@ def test_data_parallel_fused_epoch_equals_single_big_batch(exchange):
 def test_loss_api_with_nvlink_exchange():
     _need(2)
     _run(_w_loss_api, 2)
+
+
+def test_loss_api_5d_split_with_nvlink_exchange():
+    _need(2)
+    _run(_w_loss_api_5d, 2)

@@ -237,3 +237,33 @@ def test_single_point_and_no_grad():
         pb.poisson.pinn_residual_loss(m, X, f, 2.0)
     with pytest.raises(pb.PdeError):
         pb.poisson.pinn_residual_loss(pb.poisson.SolutionNet(2, 16, 3), X.cpu(), f.cpu(), 2.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_wan_scalar_losses_vs_reference_formulas(kind, dtype):
+    """pde_wan_scalars against the tensor expressions the reference's WAN losses end with (Poisson_ND.py:118-127,
+    IPW_1D_WAN.py:108-114; kind 1: KH_1D.py:263-268), values and gradients with respect to the four means."""
+    from pde_b200.ops import wan_scalar_losses
+    torch.manual_seed(kind)
+    for trial in range(4):
+        m = (torch.rand(4, dtype=torch.float64) + 0.05) * torch.tensor([1.0, 0.3, 0.02, 2.0], dtype=torch.float64)
+        m[0] = m[0] * (-1) ** trial
+        vol, reg, wp, wn, e1, e2 = 4.0 + trial, 0.7, 10.0, 3.0, (1e-8 if kind == 0 else 1e-12), 1e-8
+        mr = m.clone().requires_grad_(True)
+        if kind == 0:
+            pde = mr[0] ** 2 / (mr[1] + e1)
+        else:
+            pde = (vol * mr[0] / (vol * mr[1] + e1)) ** 2
+        lv = -torch.log(pde + e2) + reg * mr[3]
+        nrm = (vol * mr[2] - 1.0) ** 2
+        tot = wp * pde + wn * nrm
+        mg = m.to("cuda", dtype).requires_grad_(True)
+        o = wan_scalar_losses(mg, kind=kind, eps_pde=e1, eps_log=e2, vol=vol, reg=reg, w_pde=wp, w_norm=wn)
+        tol = 1e-12 if dtype == torch.float64 else 2e-6
+        for got, want in zip(o, (pde, lv, nrm, tot)):
+            assert abs(float(got.detach()) - float(want.detach())) <= tol * max(1.0, abs(float(want.detach())))
+        for got, want in ((o[3], tot), (o[1], lv), (o[0] + 2.0 * o[2], pde + 2.0 * nrm)):
+            gw, = torch.autograd.grad(want, mr, retain_graph=True)
+            gg, = torch.autograd.grad(got, mg, retain_graph=True)
+            assert float((gg.double().cpu() - gw).abs().max()) <= tol * max(1.0, float(gw.abs().max()))
