@@ -95,6 +95,12 @@ def _worker(rank, world, port, out):
     t = torch.tensor(local_F_grad * n_r / N)
     dist.all_reduce(t)
     res["ray_naive"] = t.numpy().copy()
+    # host-side defaults of the data-parallel API: the global point count when the caller gives none, and the
+    # sampler's per-rank Philox counter block
+    assert ops._global_count(151, dist.group.WORLD, None) == 151 * world
+    assert ops._global_count(151, dist.group.WORLD, 301) == 301 and ops._global_count(151, None, None) is None
+    from pde_b200.train import rank_offset
+    assert rank_offset(0) == 0 and rank_offset(rank) == rank << 40 and rank_offset(1) > 10 ** 9
     if rank == 0:
         np.savez(out, **res)
     dist.barrier()
