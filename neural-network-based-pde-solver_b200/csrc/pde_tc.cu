@@ -315,8 +315,8 @@ struct SmemMap {
   static constexpr int off_T2 = off_T1 + set_bytes;       // adjoints Zb_l (operand of dgrad / wgrad)
   static constexpr int off_W = off_T2 + set_bytes;        // W_l hi, lo (x3 layers when resident)
   static constexpr int w_bytes = (w_resident ? 3 : 1) * 2 * TILE_BYTES;
-  static constexpr int off_XT = off_W + w_bytes;          // x^T hi, lo (8 rows x 128 B each), rows j<D: x_j, row D: ones
-  static constexpr int off_E = off_XT + 2048;             // indicator tiles E_0..E_{D-1}: row n all ones
+  static constexpr int off_XT = off_W + w_bytes;          // x^T hi, lo (8 rows x 128 B each), rows j<D: x_j, row D: ones; two buffers (tile parity)
+  static constexpr int off_E = off_XT + 4096;             // indicator tiles E_0..E_{D-1}: row n all ones
   static constexpr int off_par = off_E + 1024 * (D > 0 ? D : 1);   // fp32 W0t [D][64], b [4][64], wL [64], bL(+pad)
   static constexpr int par_floats = D * 64 + 4 * 64 + 64 + 4;
   static constexpr int off_X = off_par + par_floats * 4;  // X tile [64][D]
@@ -491,8 +491,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     const int n = i / 256, w = i % 256;  // tile n, 32-bit word w: row = w / 32
     reinterpret_cast<uint32_t*>(sm + SM::off_E)[i] = ((w >> 5) == n) ? ONE_X2 : 0u;
   }
-  for (int i = tid; i < 512; i += NTHREADS) {
-    const int t = i / 256, w = i % 256;
+  for (int i = tid; i < 1024; i += NTHREADS) {
+    const int t = (i / 256) & 1, w = i % 256;   // hi, lo tile of either buffer
     reinterpret_cast<uint32_t*>(sm + SM::off_XT)[i] = (t == 0 && (w >> 5) == D) ? ONE_X2 : 0u;
   }
   {
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       // low descriptor words (start address in 16-byte units | LBO) of the K-major / MN-major views
       const uint32_t kT1K = (sT1 >> 4) | DESC_K_LBO, kT1M = (sT1 >> 4) | DESC_MN_LBO;
       const uint32_t kT2K = (sT2 >> 4) | DESC_K_LBO, kT2M = (sT2 >> 4) | DESC_MN_LBO;
-      const uint32_t kXTK = (sXT >> 4) | DESC_K_LBO, kETK = (sET >> 4) | DESC_K_LBO;
+      const uint32_t kXT0 = (sXT >> 4) | DESC_K_LBO, kETK = (sET >> 4) | DESC_K_LBO;
       uint32_t ph_chunk = 0, ph_own = 0, ph_wt = 0;
       int reg = 0;   // region the next D-producing GEMM writes
       int cur_w = 1;   // layer whose W sits in the single buffer (non-resident W)
@@ -693,6 +693,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           ph_chunk ^= 1;
           if (elect_one()) {
             const uint32_t d = tm + (16u << 16) + COL_SMALL;
+            const uint32_t kXTK = kXT0 + (((tile - tile_begin) & 1) << 7);   // this tile's x^T buffer (2048 B apart)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               mma_k(d, kT2M + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
@@ -870,18 +871,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       }
     };
     if (tile_begin < tile_end) load_x(tile_begin);
-    bool need_flush = false;   // the gradient accumulators hold a finished tile that is not in the running sums yet
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const long long base = (long long)tile * TP;
       TS(1);
-      // every MMA of the previous tile has completed before X^T / the operand sets are rewritten
-      if (w_pending) {
-        mbar_wait(bar_w, ph_w);
-        ph_w ^= 1;
-        w_pending = false;
-        tc_fence_after();
-        need_flush = true;   // added to the running sums in the shadow of the last forward layer's GEMM (below)
-      }
+      // The previous tile's first-layer MMAs may still be running: they read the adjoint set, the E tiles and the
+      // OTHER x^T buffer, none of which this tile's forward sweep writes.  They are waited for in the last forward
+      // layer, where their accumulators are added to the running sums.
+      const uint32_t sXTb = sXT + (((tile - tile_begin) & 1) << 11);
       named_sync(1, NEPI * 32);   // everyone is done with sX / sNb / sRed of the previous tile
 #pragma unroll
       for (int k = 0; k < XR; ++k)
@@ -900,8 +896,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           uint32_t hi, lo;
           split2(sX[pp * D + j], sX[(pp + 1) * D + j], hi, lo);
           const uint32_t off = tile_off(j, pp >> 3) + ((pp & 7) << 1);
-          sts32(sXT + off, hi);
-          sts32(sXT + 1024 + off, lo);
+          sts32(sXTb + off, hi);
+          sts32(sXTb + 1024 + off, lo);
         }
       }
 
@@ -918,9 +914,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         if constexpr (LAST) {
           // the previous tile's gradient accumulators: nothing writes them before this tile's reverse sweep,
           // and the wait for this layer's GEMM below would be idle time otherwise
-          if (need_flush) {
+          if (w_pending) {
+            mbar_wait(bar_w, ph_w);
+            ph_w ^= 1;
+            w_pending = false;
+            tc_fence_after();
             flush_grads();
-            need_flush = false;
           }
         }
         if constexpr (!L0) {
@@ -1434,9 +1433,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       mbar_wait(bar_w, ph_w);
       ph_w ^= 1;
       tc_fence_after();
-      need_flush = true;
+      flush_grads();
     }
-    if (need_flush) flush_grads();
     if (do_bwd) {
       const float inv = (adj_scale != 0.f) ? 1.f / adj_scale : 1.f;   // exact: a power of two
       // hidden GEMM layers: gW_l at slot l-1, rows o = 16 q + lane/4 (+8), columns i

@@ -6,13 +6,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 out = os.environ.setdefault("PDE_B200_TIMELINE", "gpurun_out/timeline.txt")
 import torch, pde_b200 as pb
 torch.manual_seed(0)
-m = pb.poisson.SolutionNet(3, 64, 5, "FBC").cuda()
+cfg3 = len(sys.argv) > 1 and sys.argv[1] == "cfg3"       # 5-D Deep Ritz (6 channels, W streamed) instead of config 2
+d = 5 if cfg3 else 3
+m = pb.poisson.SolutionNet(d, 64, 5, "RB" if cfg3 else "FBC").cuda()
 N = 1 << 20
-X = torch.rand(N, 3, device="cuda") * 2
-f = pb.poisson.rhs_f_for_u_sin(X, 2.0, [1, 1, 1])
+X = torch.rand(N, d, device="cuda") * 2
+f = pb.poisson.rhs_f_for_u_sin(X, 2.0, [1] * d)
 for _ in range(2):
     m.zero_grad()
-    l = pb.poisson.pinn_residual_loss(m, X, f, 2.0); l.backward()
+    l = (pb.poisson.drm_energy_loss if cfg3 else pb.poisson.pinn_residual_loss)(m, X, f, 2.0); l.backward()
 torch.cuda.synchronize()
 ev = [[], []]
 for line in open(out):
