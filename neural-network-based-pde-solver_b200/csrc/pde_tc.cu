@@ -59,6 +59,9 @@ constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp 
 #ifndef PDE_TC_FENCE_MASK
 #define PDE_TC_FENCE_MASK 0xF   // bit j: chunk j gets its own fence + barrier arrival (bit 3 must be set)
 #endif
+#ifndef PDE_TC_SHADOW
+#define PDE_TC_SHADOW 2         // chunk-0 shadow of the adjoint operand set (see SmemMap); 1: rebuilt A chunk 0 in a fifth pass, 2: parked in TMEM
+#endif
 #define PDE_TC_STR2(x) #x
 #define PDE_TC_STR(x) PDE_TC_STR2(x)
 #if PDE_TC_NEPI == 16
@@ -309,22 +312,38 @@ __device__ void program_point_lap(const TcArgs& a, const float* x, float fv, flo
 // ---------------------------------------------------------------- shared-memory carve-up (bytes from the 1024-aligned base)
 template <int D, int C>
 struct SmemMap {
-  static constexpr bool w_resident = (C <= 5);            // all hidden W tiles stay in smem when they fit
+  static constexpr int LIMIT = 232448;                    // dynamic shared memory a CTA can opt in to
   static constexpr int set_bytes = 2 * C * TILE_BYTES;
+  static constexpr int par_floats = D * 64 + 4 * 64 + 64 + 4;
+  static constexpr int red_floats = (2 * 64 * C > 256 * RS) ? 2 * 64 * C : 256 * RS;   // also [4 RS][64] at the end
+  // everything but the operand sets, W and the chunk-0 shadow
+  static constexpr int rest = 4096 + 1024 * (D > 0 ? D : 1) + par_floats * 4 + 64 * D * 4 + 64 * C * 4 + red_floats * 4 + 128;
+  // Chunk-0 shadow of the adjoint set (reverse sweep): columns 0..15 of the 2 C adjoint tiles in an unswizzled K-major
+  // layout (2 KB per tile), so that a reverse layer can publish its first chunk while the previous layer's wgrad still
+  // reads the adjoint set proper.  Where it only fits with two W slots, W_1 stays and W_2 / W_3 share the second slot.
+  static constexpr int shadow_if = 2 * C * 2048;
+  static constexpr bool fits3 = 2 * set_bytes + 3 * 2 * TILE_BYTES + shadow_if + rest <= LIMIT;
+  static constexpr bool fits2 = 2 * set_bytes + 2 * 2 * TILE_BYTES + shadow_if + rest <= LIMIT;
+  static constexpr bool shadow = (PDE_TC_SHADOW != 0) && (NEPI == 8) && (C <= 5) && (fits3 || fits2);
+#ifdef PDE_TC_FORCE_WS2
+  static constexpr int w_slots = (C <= 5) ? 2 : 1;   // development: two W slots whether the shadow needs them or not
+#else
+  static constexpr int w_slots = (C <= 5) ? ((shadow && !fits3) ? 2 : 3) : 1;   // 3: every hidden W resident
+#endif
   static constexpr int off_T1 = 0;                        // activations A_l (operand of fwd / wgrad)
   static constexpr int off_T2 = off_T1 + set_bytes;       // adjoints Zb_l (operand of dgrad / wgrad)
-  static constexpr int off_W = off_T2 + set_bytes;        // W_l hi, lo (x3 layers when resident)
-  static constexpr int w_bytes = (w_resident ? 3 : 1) * 2 * TILE_BYTES;
-  static constexpr int off_XT = off_W + w_bytes;          // x^T hi, lo (8 rows x 128 B each), rows j<D: x_j, row D: ones; two buffers (tile parity)
+  static constexpr int off_W = off_T2 + set_bytes;        // W_l hi, lo per slot
+  static constexpr int w_bytes = w_slots * 2 * TILE_BYTES;
+  static constexpr int off_Z0 = off_W + w_bytes;          // chunk-0 shadow of the adjoint set
+  static constexpr int off_XT = off_Z0 + (shadow ? shadow_if : 0);   // x^T hi, lo (8 rows x 128 B each), rows j<D: x_j, row D: ones; two buffers (tile parity)
   static constexpr int off_E = off_XT + 4096;             // indicator tiles E_0..E_{D-1}: row n all ones
   static constexpr int off_par = off_E + 1024 * (D > 0 ? D : 1);   // fp32 W0t [D][64], b [4][64], wL [64], bL(+pad)
-  static constexpr int par_floats = D * 64 + 4 * 64 + 64 + 4;
   static constexpr int off_X = off_par + par_floats * 4;  // X tile [64][D]
   static constexpr int off_nb = off_X + 64 * D * 4;       // cotangents of the network jets [64][C]
   static constexpr int off_red = off_nb + 64 * C * 4;     // output-layer partial sums [2][64][C]
-  static constexpr int red_floats = (2 * 64 * C > 256 * RS) ? 2 * 64 * C : 256 * RS;   // also [4 RS][64] at the end
   static constexpr int off_bar = off_red + red_floats * 4;
   static constexpr int total = off_bar + 128;
+  static_assert(total <= LIMIT, "shared-memory plan does not fit");
 };
 
 // explicit state-space accesses (pointers reached through the argument struct are generic otherwise)
@@ -458,7 +477,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   constexpr int NV = 2 + ND + LAP;  // stashed values per (point, unit, layer)
   static_assert(C <= MAXC, "too many jet channels for the TMEM / smem budget");
   using SM = SmemMap<D, C>;
-  constexpr bool WRES = SM::w_resident;
+  constexpr int WS = SM::w_slots;
+  constexpr bool WRES = (WS == 3);
+  constexpr bool SHADOW = SM::shadow;
+  constexpr bool SHADOW_TAIL = SHADOW && (PDE_TC_SHADOW == 1);   // fifth pass + bar_fix hand-shake
 
   extern __shared__ __align__(1024) unsigned char sm[];
   float* sPar = reinterpret_cast<float*>(sm + SM::off_par);
@@ -474,6 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   uint64_t* bar_own = bar_chunk + 6;   // issuer-private: "everything I issued so far has completed"
   uint64_t* bar_wt = bar_chunk + 7;    // bulk copy of a W tile pair has landed (non-resident W only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_chunk + 8);
+  uint64_t* bar_fix = bar_chunk + 9;   // 8 arrivals, epilogue -> issuer: chunk 0 of both operand sets is in place (shadow builds)
   float* sMx = reinterpret_cast<float*>(bar_chunk + 10);   // per-tile maximum cotangent of warps 0 and 1
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -482,8 +505,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   const bool do_bwd = a.want_grad != 0;
   const uint32_t sbase = smem_u32(sm);
   const uint32_t sT1 = sbase + SM::off_T1, sT2 = sbase + SM::off_T2, sWT = sbase + SM::off_W;
-  const uint32_t sXT = sbase + SM::off_XT, sET = sbase + SM::off_E;
+  const uint32_t sXT = sbase + SM::off_XT, sET = sbase + SM::off_E, sZ0 = sbase + SM::off_Z0;
 
+  // W slots: 3 = layer l in slot l-1; 1 = one slot for all, refilled before every GEMM layer; 2 = W_2 stays in slot 0,
+  // W_1 and W_3 take turns in slot 1: each is fetched a whole layer before it is needed (W_3 once the forward GEMM of
+  // layer 1 has completed, W_1 once dgrad_3 has), so that copy is never waited for.
+  auto w_addr = [&](int l) { return sWT + (WS == 3 ? l - 1 : (WS == 2 ? (l == 2 ? 0 : 1) : 0)) * 2 * TILE_BYTES; };
   // ---- one-time setup (all warps)
   for (int i = tid; i < D * 64 + n_h * 64; i += NTHREADS) sPar[i] = a.params[i];
   for (int i = tid; i < 64 + 1; i += NTHREADS) sWL[i] = a.params[D * 64 + n_h * 64 + i];
@@ -499,7 +526,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     // resident: every hidden layer's W; otherwise W_1 (later layers are streamed by the issuer)
     const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
     uint4* dst = reinterpret_cast<uint4*>(sm + SM::off_W);
-    for (int i = tid; i < (WRES ? n_h - 1 : 1) * 2 * TILE_BYTES / 16; i += NTHREADS) dst[i] = src[i];
+    for (int l = 1; l <= (n_h - 1 < WS ? n_h - 1 : WS); ++l) {
+      dst = reinterpret_cast<uint4*>(sm + SM::off_W + (w_addr(l) - sWT));
+      for (int i = tid; i < 2 * TILE_BYTES / 16; i += NTHREADS) dst[i] = src[(l - 1) * (2 * TILE_BYTES / 16) + i];
+    }
   }
   if (tid == 0) {
     for (int j = 0; j < 4; ++j) mbar_init(&bar_chunk[j], NEPI);
@@ -507,6 +537,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     mbar_init(bar_w, 1);
     mbar_init(bar_own, 1);
     mbar_init(bar_wt, 1);
+    mbar_init(bar_fix, NEPI);
     fence_mbar_init();
     if (sbase & 1023u) __trap();   // SWIZZLE_128B tiles need the 1024-byte alignment the declaration asks for
   }
@@ -536,7 +567,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #endif
   // accumulator address of jet channel c in region r: pair c/2 at columns 64 (c/2), lane half c%2
   auto d_addr = [&](int r, int c) { return taddr_of(tmem, 16 * (c & 1), COL_R0 + 192 * r + 64 * (c >> 1)); };
-  auto w_addr = [&](int l) { return sWT + (WRES ? (l - 1) * 2 * TILE_BYTES : 0); };
 
   if (warp >= NEPI) {
     // =====================================================================================
@@ -555,9 +585,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       const uint32_t kT1K = (sT1 >> 4) | DESC_K_LBO, kT1M = (sT1 >> 4) | DESC_MN_LBO;
       const uint32_t kT2K = (sT2 >> 4) | DESC_K_LBO, kT2M = (sT2 >> 4) | DESC_MN_LBO;
       const uint32_t kXT0 = (sXT >> 4) | DESC_K_LBO, kETK = (sET >> 4) | DESC_K_LBO;
-      uint32_t ph_chunk = 0, ph_own = 0, ph_wt = 0;
+      uint32_t ph_chunk = 0, ph_own = 0, ph_wt = 0, ph_fix = 0;
       int reg = 0;   // region the next D-producing GEMM writes
-      int cur_w = 1;   // layer whose W sits in the single buffer (non-resident W)
+      int cur_w = 1;   // layer whose W sits in the shared slot (non-resident W)
+      // chunk-0 shadow (unswizzled K-major: LBO 128 = next core matrix along K, SBO 256 = next 8 rows)
+      const uint32_t kZ0 = (sZ0 >> 4) | ((128u >> 4) << 16);
+      constexpr uint32_t DESC_HI_Z0 = (256u >> 4) | (1u << 14);
       // Non-resident W (6 channels): one tile-pair buffer, refilled with a bulk copy.  need_w(l) makes W_l current:
       // drain my MMAs (they may read the buffer), copy, wait.  In the reverse sweep the copy of W_{l-1} is started as
       // soon as dgrad_l has completed — wgrad_l, which runs for another ~2.6 k cycles, does not read W — so only its
@@ -566,7 +599,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       auto start_w_load = [&](int l) {
         if (elect_one()) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar_wt)), "r"(2 * TILE_BYTES) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWT),
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(w_addr(l)),
                        "l"(a.wimg + (size_t)(l - 1) * 2 * TILE_BYTES), "r"(2 * TILE_BYTES), "r"(smem_u32(bar_wt))
                        : "memory");
         }
@@ -576,6 +609,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       };
       auto need_w = [&](int l) {
         if (WRES) return;
+        if (WS == 2 && l == 2) return;
+        // (two slots: the copy was normally started a layer ago, see below, and only its arrival is waited for;
+        //  forward-only launches find W_3 in the slot when the next tile asks for W_1 and take the slow way)
         if (cur_w != l) {
           if (elect_one()) mma_commit(bar_own);
           __syncwarp();
@@ -600,6 +636,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             mbar_wait(&bar_chunk[j], ph_chunk);
             tc_fence_after();
             TS(100 + 10 * l + j);
+            // the epilogue has consumed the accumulators of layer 1, so nothing reads W_1 any more
+            if (WS == 2 && j == 0 && l == 2 && n_h - 1 == 3) start_w_load(3);
             if (elect_one()) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
@@ -628,8 +666,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             mbar_wait(&bar_chunk[j], ph_chunk);
             tc_fence_after();
             TS(200 + 10 * l + j);
+            if (WS == 2 && j == 0 && l == 2 && n_h - 1 == 3) start_w_load(1);   // dgrad_3 has been consumed
             // dgrad: Ab_{l-1,c} += Zb_{l,c}[:, K step j] W_l[K step j, :]
-            if (elect_one()) {
+            if (SHADOW && j == 0 && l < n_h - 1) {
+              // below the top layer the first chunk of the adjoints sits in the shadow
+              if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                  const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
+                  const uint32_t zh = kZ0 + (2 * c) * (2048 >> 4), zl = zh + (2048 >> 4);
+                  mma_k(d, zh, DESC_HI_Z0, kW, DESC_HI, ID_DG, 0u);
+                  mma_k(d, zl, DESC_HI_Z0, kW, DESC_HI, ID_DG, 1u);
+                  mma_k(d, zh, DESC_HI_Z0, kW + TD, DESC_HI, ID_DG, 1u);
+                }
+              }
+            } else if (elect_one()) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
                 const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
@@ -641,13 +692,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
             __syncwarp();
           }
+          const bool refill_next = (WS == 1) && l > 1;
           if (elect_one()) {
             mma_commit(bar_d);
-            if (!WRES && l > 1) mma_commit(bar_own);   // "dgrad_l has completed": the W buffer may be refilled
+            if (refill_next) mma_commit(bar_own);   // "dgrad_l has completed": the W buffer may be refilled
           }
           __syncwarp();
           ph_chunk ^= 1;
           reg ^= 1;
+          if (SHADOW_TAIL && l < n_h - 1) {
+            // chunk 0 of the adjoints has been copied from the shadow and chunk 0 of A_{l-1} rebuilt
+            mbar_wait(bar_fix, ph_fix);
+            ph_fix ^= 1;
+            tc_fence_after();
+          }
           // wgrad: gW_l(tile) = sum_c Zb_{l,c}^T A_{l-1,c}   (K = 64 points);  bias: gb_l(tile) = Zb_{l,0}^T 1.
           // The accumulators start from zero every tile (the epilogue adds them to the running fp32
           // sums, see flush_grads) and the small cross terms go first: the tensor core truncates
@@ -679,7 +737,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             mma_commit(bar_w);
           }
           __syncwarp();
-          if (!WRES && l > 1) {
+          if (refill_next) {
             mbar_wait(bar_own, ph_own);
             ph_own ^= 1;
             start_w_load(l - 1);   // under wgrad_l
@@ -689,6 +747,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         {
 #pragma unroll
           for (int j = 0; j < 4; ++j) mbar_wait(&bar_chunk[j], ph_chunk);
+          if (SHADOW_TAIL) {
+            mbar_wait(bar_fix, ph_fix);
+            ph_fix ^= 1;
+          }
           tc_fence_after();
           ph_chunk ^= 1;
           if (elect_one()) {
@@ -786,6 +848,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         else stsm_x2(addr + c * 2 * TILE_BYTES, pk[c][0], pk[c][1]);
       }
     };
+    // chunk 0 of the adjoints into the shadow (unswizzled: 8-row group g at 256 g, K half h at +128, row at +16 (row & 7))
+    const uint32_t z0_base = sZ0 + (uint32_t)(sm_tile * 2048) + ((sm_row >> 3) << 8) + (h << 7) + ((sm_row & 7) << 4);
+    auto put_shadow = [&](const uint32_t (&pk)[C][NE]) {
+      if constexpr (RS == 1) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) stsm_x4(z0_base + c * 4096, pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+      }
+    };
+    // ... and from there into the adjoint set proper: every warp moves the 16 rows x 16 bytes per tile it wrote itself
+    auto copy_shadow = [&]() {
+      const int t = lane >> 4, row = 16 * q + (lane & 15);
+      const uint32_t src = sZ0 + (uint32_t)(t * 2048) + ((row >> 3) << 8) + (h << 7) + ((row & 7) << 4);
+      const uint32_t dst = sT2 + (uint32_t)(t * TILE_BYTES) + tile_off(row, h);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src + c * 4096) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + c * 2 * TILE_BYTES), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+      }
+    };
+    const uint32_t park = taddr_of(tmem, 32 * q + 16, COL_R0 + 192 * h + 128);
     auto store_chunk = [&](uint32_t set, int j, const float (&v)[C][NE]) {
       uint32_t pk[C][NE];
       pack_chunk(v, pk);
@@ -1191,8 +1275,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
           }
         };
+        // Shadow builds, below the top layer (SH): chunk 0 of the adjoints goes to the shadow, so nothing waits for
+        // the previous layer's wgrad before chunk 1; chunk 0 of the rebuilt A_{l-1} is made last (a fifth pass that
+        // also copies the shadow into the adjoint set), in the shadow of the last dgrad K step.
+        constexpr bool SH = SHADOW && !TOP;
+        constexpr bool SHT = SHADOW_TAIL && !TOP;   // chunk 0 of A_{l-1} rebuilt in a fifth pass
+        constexpr bool SHP = SH && !SHT;            // ... rebuilt in the first pass and parked in TMEM until the sets are free
         load_cur(0);
-        load_prv(0);
+        load_prv(SHT ? 1 : 0);
         TS(30 + l);
         if constexpr (!TOP) {
           mbar_wait(bar_d, ph_d);   // Ab_l is complete
@@ -1214,9 +1304,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
           for (int c = 0; c < C; ++c) tmem_ld_16x256b(absrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1), abr[c]);
         }
+        auto refill = [&](const int u0, float (&ap)[C][NE]) {
+          // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
+          float pv0[NE], pv1[NE];
+          to_arr(prv[0], pv0);
+          to_arr(prv[1], pv1);
+          float zp[C][NE];
+          if constexpr (LK >= 2) {
+#pragma unroll
+            for (int c = 1; c < C; ++c) to_arr(prv[1 + c], zp[c]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+              const int u = u0 + (e & 1);
+#pragma unroll
+              for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[(dir0 + i) * 64 + u];
+              if constexpr (LAP) zp[1 + ND][e] = 0.f;
+            }
+          }
+          if constexpr (PDE_TC_F32X2 && NE % 2 == 0 && ND >= 1) {
+#pragma unroll
+            for (int e = 0; e < NE; e += 2) {
+              float s0a, s1a, s2a, s3a, s0b, s1b, s2b, s3b;
+              act_from_stash(act, pv0[e], pv1[e], s0a, s1a, s2a, s3a);
+              act_from_stash(act, pv0[e + 1], pv1[e + 1], s0b, s1b, s2b, s3b);
+              ap[0][e] = s0a; ap[0][e + 1] = s0b;
+              const f32x2 S1 = pk2(s1a, s1b);
+              f32x2 S = 0;
+#pragma unroll
+              for (int i = 0; i < ND; ++i) {
+                const f32x2 Z = pk2(zp[1 + i][e], zp[1 + i][e + 1]);
+                unpk2(mul2(S1, Z), ap[1 + i][e], ap[1 + i][e + 1]);
+                S = (i == 0) ? mul2(Z, Z) : fma2(Z, Z, S);
+              }
+              if constexpr (LAP)
+                unpk2(fma2(S1, pk2(zp[1 + ND][e], zp[1 + ND][e + 1]), mul2(pk2(s2a, s2b), S)), ap[1 + ND][e], ap[1 + ND][e + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+              float s0, s1, s2, s3;
+              act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
+              ap[0][e] = s0;
+              float S = 0.f;
+#pragma unroll
+              for (int i = 0; i < ND; ++i) {
+                ap[1 + i][e] = s1 * zp[1 + i][e];
+                S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
+              }
+              if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
+            }
+          }
+        };
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const int u0 = 16 * j + 8 * h + cq;
+          uint32_t zk[C][NE];
+          {
           if constexpr (TOP) {
             const float w0v = sWL[u0], w1v = sWL[u0 + 1];
 #pragma unroll
@@ -1346,64 +1490,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               for (int v = 0; v < ((LK >= 1) ? NV : 2); ++v) stash_discard(stash_at(l, j, v));
             }
           }
-          uint32_t zk[C][NE];
           pack_chunk(zb, zk);
-          float ap[C][NE];
-          if constexpr (REFILL) {
-            // activations of layer l-1 (operand of this layer's wgrad) recomputed from its stash
-            float pv0[NE], pv1[NE];
-            to_arr(prv[0], pv0);
-            to_arr(prv[1], pv1);
-            float zp[C][NE];
-            if constexpr (LK >= 2) {
-#pragma unroll
-              for (int c = 1; c < C; ++c) to_arr(prv[1 + c], zp[c]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < NE; ++e) {
-                const int u = u0 + (e & 1);
-#pragma unroll
-                for (int i = 0; i < ND; ++i) zp[1 + i][e] = sW0t[(dir0 + i) * 64 + u];
-                if constexpr (LAP) zp[1 + ND][e] = 0.f;
-              }
-            }
-            if constexpr (PDE_TC_F32X2 && NE % 2 == 0 && ND >= 1) {
-#pragma unroll
-              for (int e = 0; e < NE; e += 2) {
-                float s0a, s1a, s2a, s3a, s0b, s1b, s2b, s3b;
-                act_from_stash(act, pv0[e], pv1[e], s0a, s1a, s2a, s3a);
-                act_from_stash(act, pv0[e + 1], pv1[e + 1], s0b, s1b, s2b, s3b);
-                ap[0][e] = s0a; ap[0][e + 1] = s0b;
-                const f32x2 S1 = pk2(s1a, s1b);
-                f32x2 S = 0;
-#pragma unroll
-                for (int i = 0; i < ND; ++i) {
-                  const f32x2 Z = pk2(zp[1 + i][e], zp[1 + i][e + 1]);
-                  unpk2(mul2(S1, Z), ap[1 + i][e], ap[1 + i][e + 1]);
-                  S = (i == 0) ? mul2(Z, Z) : fma2(Z, Z, S);
-                }
-                if constexpr (LAP)
-                  unpk2(fma2(S1, pk2(zp[1 + ND][e], zp[1 + ND][e + 1]), mul2(pk2(s2a, s2b), S)), ap[1 + ND][e], ap[1 + ND][e + 1]);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < NE; ++e) {
-                float s0, s1, s2, s3;
-                act_from_stash(act, pv0[e], pv1[e], s0, s1, s2, s3);
-                ap[0][e] = s0;
-                float S = 0.f;
-#pragma unroll
-                for (int i = 0; i < ND; ++i) {
-                  ap[1 + i][e] = s1 * zp[1 + i][e];
-                  S = fmaf(zp[1 + i][e], zp[1 + i][e], S);
-                }
-                if constexpr (LAP) ap[1 + ND][e] = fmaf(s1, zp[1 + ND][e], s2 * S);
-              }
-            }
-            if (j < 3) load_prv(j + 1);
           }
-          if (j == 0 && w_pending) {
-            // the previous layer's wgrad still reads both operand sets: both results of chunk 0 are
+          float ap[C][NE];
+          if (REFILL && (!SHT || j > 0)) {
+            refill(u0, ap);
+            if constexpr (SHT) load_prv(j < 3 ? j + 1 : 0);
+            else if (j < 3) load_prv(j + 1);
+          }
+          // first layer (no GEMM consumes its chunks one by one): chunk 1 is parked as well and the wait moves to chunk 2
+          constexpr bool SHP0 = SHP && LK == 0;
+          if (j == (SH ? (SHP0 ? 2 : 1) : 0) && w_pending) {
+            // the previous layer's wgrad still reads both operand sets: the results of this chunk are
             // computed before waiting for it, the stores come after
             TS(50 + l);
             mbar_wait(bar_w, ph_w);
@@ -1411,9 +1509,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             w_pending = false;
             TS(60 + l);
           }
-          put_chunk(sT2, j, zk);
-          if constexpr (REFILL) store_chunk(sT1, j, ap);
+          if (SHP0 && j <= 2) {
+            if (j == 0) {
+              put_shadow(zk);
+            } else if (j == 1) {
+#pragma unroll
+              for (int c = 0; c < C; ++c) tmem_st_16x256b_u32(park + 8 * c, zk[c]);
+              tmem_st_wait();
+            } else {
+              put_chunk(sT2, 2, zk);
+              uint32_t pk[C][NE];
+#pragma unroll
+              for (int c = 0; c < C; ++c) tmem_ld_16x256b_u32(park + 8 * c, pk[c]);
+              tmem_ld_wait();
+              put_chunk(sT2, 1, pk);
+              copy_shadow();
+              chunk_done(2);   // publishes chunks 0..2
+            }
+            continue;
+          }
+          if (SH && j == 0) {
+            put_shadow(zk);
+            if constexpr (SHP && REFILL) {
+              // park the split A_{l-1} chunk in the unused accumulator slot of region h (lane half 1, columns 128..)
+              uint32_t pk[C][NE];
+              pack_chunk(ap, pk);
+#pragma unroll
+              for (int c = 0; c < C; ++c) tmem_st_16x256b_u32(park + 8 * c, pk[c]);
+              tmem_st_wait();
+            }
+          } else {
+            put_chunk(sT2, j, zk);
+            if constexpr (REFILL) store_chunk(sT1, j, ap);
+            if (SHP && j == 1) {
+              // the sets are free: chunk 0 moves from the shadow / TMEM to its place
+              if constexpr (REFILL) {
+                uint32_t pk[C][NE];
+#pragma unroll
+                for (int c = 0; c < C; ++c) tmem_ld_16x256b_u32(park + 8 * c, pk[c]);
+                tmem_ld_wait();
+                put_chunk(sT1, 0, pk);
+              }
+              copy_shadow();
+            }
+          }
           chunk_done(j);
+        }
+        if constexpr (SHT) {
+          // chunk 0 of both operand sets, in the shadow of the last dgrad K step
+          if constexpr (REFILL) {
+            float ap[C][NE];
+            refill(8 * h + cq, ap);
+            store_chunk(sT1, 0, ap);
+          }
+          copy_shadow();
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_fix);
         }
         if constexpr (!TOP) reg ^= 1;
         w_pending = true;   // the issuer commits bar_w after this step's wgrad / first-layer MMAs

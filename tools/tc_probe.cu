@@ -22,6 +22,8 @@ using namespace pde::tc;
 // modes: 0 A K-major, B K-major | 1 A K-major, B MN-major | 2 A MN-major, B MN-major
 //        3 = mode 0 but D at lane offset 16, column 64 | 4 = N=8 K-major B
 //        5 = A MN-major, B MN-major N=16 slice at column offset 32 of the B tile (wgrad^T chunk)
+//        6 = A K-major WITHOUT swizzle, one 2 KB block per K step: core matrix (8 rows x 16 B) of row group g, K half k at
+//            256 g + 128 k (LBO 128, SBO 256); B as in mode 0
 struct Args {
   const float* A;  // [64][64] logical "row-major as stored in the tile"
   const float* B;  // [64][64]
@@ -46,6 +48,13 @@ __global__ void __launch_bounds__(128, 1) probe(Args a) {
     *reinterpret_cast<op_t*>(tA + tile_off(r, c >> 3) + (c & 7) * 2) = va;
     *reinterpret_cast<op_t*>(tB + tile_off(r, c >> 3) + (c & 7) * 2) = vb;
   }
+  if (a.mode == 6) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 64; i += 128) {
+      int r = i / 64, c = i % 64, ks = c >> 4, k = (c >> 3) & 1;
+      *reinterpret_cast<op_t*>(tA + ks * 2048 + (r >> 3) * 256 + k * 128 + (r & 7) * 16 + (c & 7) * 2) = TO_OP(a.A[i]);
+    }
+  }
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   fence_proxy_async();
@@ -64,6 +73,11 @@ __global__ void __launch_bounds__(128, 1) probe(Args a) {
     const uint32_t d = taddr_of(tb, lane_off, col_off);
     for (int ks = 0; ks < 4; ++ks) {
       uint64_t ad = a_mn ? desc_mnmajor(smem_u32(tA), ks) : desc_kmajor(smem_u32(tA), ks);
+      if (a.mode == 6) {   // no swizzle: layout type 0, LBO 128 (next core matrix along K), SBO 256 (next 8 rows)
+        const uint32_t sa = smem_u32(tA) + ks * 2048;
+        ad = static_cast<uint64_t>((sa & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(128 >> 4) << 16) | (static_cast<uint64_t>(256 >> 4) << 32) |
+             (static_cast<uint64_t>(1) << 46);
+      }
       uint64_t bd = b_mn ? desc_mnmajor(smem_u32(tB) + (a.mode == 5 ? 64 : 0), ks) : desc_kmajor(smem_u32(tB), ks);
       mma_bf16(d, ad, bd, idesc, ks > 0);
     }
@@ -111,7 +125,7 @@ int main() {
   cudaMemcpy(dB, B.data(), 16384, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE_BYTES + 1024);
   int fails = 0;
-  for (int mode = 0; mode <= 5; ++mode) {
+  for (int mode = 0; mode <= 6; ++mode) {
     cudaMemset(dD, 0, 16384); cudaMemset(dR, 0, 32768);
     Args a{dA, dB, dD, dR, mode};
     probe<<<1, 128, 2 * TILE_BYTES + 1024>>>(a);
