@@ -222,26 +222,38 @@ __device__ __forceinline__ void act_eval(int act, const float (&z)[N], bool big,
 // ---------------------------------------------------------------- envelope + residual program on (value, grad, Lap) jets
 // nj: network jets in, cotangents out.  Follows program_point in pde_simt.cuh with the Hessian
 // diagonal replaced by its sum.
+// The envelope's own jet (B, dB/dx_i, Lap B) depends on the point only: the kernel evaluates it while it waits for the
+// first hidden GEMM (envelope_point, into the slots the cotangents take later) and the residual stage reads it back.
 template <int D, int ORDER>
-__device__ void program_point_lap(const TcArgs& a, const float* x, float fv, float bt, float (&nj)[1 + (ORDER >= 1 ? D : 0) + (ORDER == 2)],
-                                  double (&qs)[4], double& gE) {
-  constexpr int ND = (ORDER >= 1) ? D : 0;
+__device__ void envelope_point(const TcArgs& a, const float* x, float* out) {
   float b[D], b1[D], b2[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) envelope_factor<float>(a.env, i, x[i], b[i], b1[i], b2[i]);
   float B = 1.f;
 #pragma unroll
   for (int i = 0; i < D; ++i) B *= b[i];
-  float Bi[D], LB = 0.f;
+  float LB = 0.f;
+  out[0] = B;
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     float e = 1.f;
 #pragma unroll
     for (int j = 0; j < D; ++j)
       if (j != i) e *= b[j];
-    Bi[i] = b1[i] * e;
+    if constexpr (ORDER >= 1) out[1 + i] = b1[i] * e;
     LB += b2[i] * e;
   }
+  if constexpr (ORDER == 2) out[1 + D] = LB;
+}
+template <int D, int ORDER>
+__device__ void program_point_lap(const TcArgs& a, const float* env, const float* cst, float fv, float bt,
+                                  float (&nj)[1 + (ORDER >= 1 ? D : 0) + (ORDER == 2)], double (&qs)[4], double& gE) {
+  constexpr int ND = (ORDER >= 1) ? D : 0;
+  const float B = env[0];
+  float Bi[D], LB = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) Bi[i] = (ORDER >= 1) ? env[1 + i] : 0.f;
+  if constexpr (ORDER == 2) LB = env[1 + D];
   const float N0 = nj[0];
   const float u = B * N0;
   float ui[D];
@@ -257,8 +269,7 @@ __device__ void program_point_lap(const TcArgs& a, const float* x, float fv, flo
 #pragma unroll
     for (int i = 0; i < D; ++i) lap += 2.f * Bi[i] * nj[1 + i];
   }
-  const float E = a.energy ? a.energy[0] : a.energy_const;
-  const float w0 = (a.seed ? a.seed[0] : 1.f) * a.inv_n;
+  const float E = cst[0], w0 = cst[1];   // energy, seed[0] / n (read from global memory once per CTA)
   float ub = 0.f, lapb = 0.f, uib[D];
 #pragma unroll
   for (int i = 0; i < D; ++i) uib[i] = 0.f;
@@ -283,7 +294,7 @@ __device__ void program_point_lap(const TcArgs& a, const float* x, float fv, flo
     for (int i = 0; i < D; ++i) g2 += ui[i] * ui[i];
     qs[0] += (double)(a.alpha * g2 + bt * u * u);
     qs[1] += (double)(u * u);
-    const float w1 = (a.seed ? a.seed[1] : 1.f) * a.inv_n;
+    const float w1 = cst[2];
     ub = 2.f * bt * u * w0 + 2.f * u * w1;
 #pragma unroll
     for (int i = 0; i < D; ++i) uib[i] = 2.f * a.alpha * ui[i] * w0;
@@ -514,6 +525,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   // ---- one-time setup (all warps)
   for (int i = tid; i < D * 64 + n_h * 64; i += NTHREADS) sPar[i] = a.params[i];
   for (int i = tid; i < 64 + 1; i += NTHREADS) sWL[i] = a.params[D * 64 + n_h * 64 + i];
+  if (tid == 0 && a.mode == 0) {
+    // loop-invariant scalars of the residual stage
+    sWL[65] = a.energy ? a.energy[0] : a.energy_const;
+    sWL[66] = (a.seed ? a.seed[0] : 1.f) * a.inv_n;
+    sWL[67] = (a.seed && a.prog == PDE_PROG_RAYLEIGH ? a.seed[1] : 1.f) * a.inv_n;
+  }
   for (int i = tid; i < (1024 * (D > 0 ? D : 1)) / 4; i += NTHREADS) {
     const int n = i / 256, w = i % 256;  // tile n, 32-bit word w: row = w / 32
     reinterpret_cast<uint32_t*>(sm + SM::off_E)[i] = ((w >> 5) == n) ? ONE_X2 : 0u;
@@ -562,8 +579,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       ++dbg_n;
     }
   };
+  // every epilogue warp: arrival at the CTA-wide barriers (id, clock), 500 events per warp
+  int dbgw_n = 0;
+  auto TSW = [&](int id) {
+    if (a.dbg && blockIdx.x == 0 && lane == 0 && warp < NEPI && dbgw_n < 500) {
+      long long* p = a.dbg + 8192 + warp * 1024 + 2 * dbgw_n;
+      p[0] = id; p[1] = clock64();
+      ++dbgw_n;
+    }
+  };
 #else
   auto TS = [](int) {};
+  auto TSW = [](int) {};
 #endif
   // accumulator address of jet channel c in region r: pair c/2 at columns 64 (c/2), lane half c%2
   auto d_addr = [&](int r, int c) { return taddr_of(tmem, 16 * (c & 1), COL_R0 + 192 * r + 64 * (c >> 1)); };
@@ -958,6 +985,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const long long base = (long long)tile * TP;
       TS(1);
+      TSW(1);
       // The previous tile's first-layer MMAs may still be running: they read the adjoint set, the E tiles and the
       // OTHER x^T buffer, none of which this tile's forward sweep writes.  They are waited for in the last forward
       // layer, where their accumulators are added to the running sums.
@@ -1007,6 +1035,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
         }
         if constexpr (!L0) {
+          if constexpr (!SPLIT) {
+            // the envelope's jet at this thread's point, while the first hidden GEMM finishes; it sits in the
+            // cotangent slots (free until the residual stage, which overwrites them with the cotangents)
+            if (l == 1 && a.mode == 0 && tid < TP) envelope_point<D, ORDER>(a, sX + tid * D, sNb + tid * C);
+          }
           mbar_wait(bar_d, ph_d);
           ph_d ^= 1;
           tc_fence_after();
@@ -1162,6 +1195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           for (int r = 0; r < NR; ++r) sRed[(h * 64 + rows[r]) * C + c] = outacc[r][c];
         }
       }
+      TSW(2);
       named_sync(1, NEPI * 32);
       float nj[C];
       if (tid < TP) {
@@ -1188,7 +1222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         if (!programmed) {
           if constexpr (!SPLIT) {
             if (gp < a.n) {
-              program_point_lap<D, ORDER>(a, sX + tid * D, fv, bt, nj, qs, gE);
+              program_point_lap<D, ORDER>(a, sNb + tid * C, sWL + 65, fv, bt, nj, qs, gE);
             } else {
 #pragma unroll
               for (int c = 0; c < C; ++c) nj[c] = 0.f;
@@ -1219,7 +1253,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
           if (lane == 0) sMx[warp] = mx;
         }
+        TSW(3);
         named_sync(1, NEPI * 32);
+        TSW(4);
         mx = fmaxf(sMx[0], sMx[1]);
         const float sm = adj_scale * mx;
         if (mx > 1e-30f && mx < 3.0e38f && (adj_scale == 0.f || sm > 256.f || sm < 0.0625f)) {
@@ -1682,6 +1718,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 __global__ void pinn_split_kernel(const TcArgs a, const float* JA, const float* JB, float* JbarA, float* JbarB, double* psums) {
   double qs[4] = {0.0, 0.0, 0.0, 0.0};
   double gE = 0.0;
+  const float cst[3] = {a.energy ? a.energy[0] : a.energy_const, (a.seed ? a.seed[0] : 1.f) * a.inv_n,
+                        (a.seed && a.prog == PDE_PROG_RAYLEIGH ? a.seed[1] : 1.f) * a.inv_n};
   for (long long gp = blockIdx.x * (long long)blockDim.x + threadIdx.x; gp < a.n; gp += (long long)gridDim.x * blockDim.x) {
     float x[5], nj[7];
 #pragma unroll
@@ -1692,7 +1730,9 @@ __global__ void pinn_split_kernel(const TcArgs a, const float* JA, const float* 
     nj[6] = JA[gp * 5 + 4] + JB[gp * 4 + 3];
     const float fv = a.f ? a.f[gp] : 0.f;
     const float bt = a.beta ? a.beta[gp] : a.beta_const;
-    program_point_lap<5, 2>(a, x, fv, bt, nj, qs, gE);
+    float env[7];
+    envelope_point<5, 2>(a, x, env);
+    program_point_lap<5, 2>(a, env, cst, fv, bt, nj, qs, gE);
     if (JbarA) {
       // the value channel's cotangent goes to pass A only (the reverse sweep is linear in the cotangents)
       JbarA[gp * 5] = nj[0]; JbarA[gp * 5 + 1] = nj[1]; JbarA[gp * 5 + 2] = nj[2]; JbarA[gp * 5 + 3] = nj[3]; JbarA[gp * 5 + 4] = nj[6];
@@ -1844,20 +1884,23 @@ static int path_override() {
 static long long* timeline_buffer() {
   static long long* buf = nullptr;
   if (!getenv("PDE_B200_TIMELINE")) return nullptr;
-  if (!buf && cudaMalloc(&buf, 8192 * sizeof(long long)) != cudaSuccess) return nullptr;
-  cudaMemset(buf, 0, 8192 * sizeof(long long));
+  if (!buf && cudaMalloc(&buf, 16384 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemset(buf, 0, 16384 * sizeof(long long));
   return buf;
 }
 static void timeline_dump(long long* buf, cudaStream_t st) {
   if (!buf) return;
   cudaStreamSynchronize(st);
-  static long long host[8192];
+  static long long host[16384];
   cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
   FILE* f = fopen(getenv("PDE_B200_TIMELINE"), "w");
   if (!f) return;
   for (int w = 0; w < 2; ++w)
     for (int i = 0; i < 2000 && host[w * 4096 + 2 * i] != 0; ++i)
       fprintf(f, "%d %lld %lld\n", w, host[w * 4096 + 2 * i], host[w * 4096 + 2 * i + 1]);
+  for (int w = 0; w < 8; ++w)
+    for (int i = 0; i < 500 && host[8192 + w * 1024 + 2 * i] != 0; ++i)
+      fprintf(f, "%d %lld %lld\n", 10 + w, host[8192 + w * 1024 + 2 * i], host[8192 + w * 1024 + 2 * i + 1]);
   fclose(f);
 }
 #endif

@@ -17,9 +17,13 @@ for _ in range(2):
     l = (pb.poisson.drm_energy_loss if cfg3 else pb.poisson.pinn_residual_loss)(m, X, f, 2.0); l.backward()
 torch.cuda.synchronize()
 ev = [[], []]
+wev = {}
 for line in open(out):
     w, i, c = line.split()
-    ev[int(w)].append((int(i), int(c)))
+    if int(w) >= 10:
+        wev.setdefault(int(w) - 10, []).append((int(i), int(c)))
+    else:
+        ev[int(w)].append((int(i), int(c)))
 names = {1: "tile start", 2: "program done"}
 for k in range(5):
     names[10 + k] = f"F{k} enter"; names[20 + k] = f"F{k} D ready"; names[30 + k] = f"B{k} enter"; names[40 + k] = f"B{k} Ab ready"
@@ -40,3 +44,17 @@ if len(starts) > 6:
     for id_, c in ev[1]:
         if t0 <= c <= e[b][1]:
             print(f"  {id_:4d} {c - t0:8d}")
+
+if wev:
+    # arrival of every epilogue warp at the CTA-wide barriers, relative to the first warp to arrive
+    print("per-warp arrival at the barriers (cycles after the first warp; id 1: tile start, 2: end of forward, 3: residual stage, 4: after it)")
+    nt = min(len([1 for i, _ in wev[w] if i == 1]) for w in wev)
+    for t in range(3, min(nt, 9)):
+        for bid in (1, 2, 3, 4):
+            arr = []
+            for w in sorted(wev):
+                xs = [c for i, c in wev[w] if i == bid]
+                if t < len(xs):
+                    arr.append(xs[t])
+            if arr:
+                print(f"  tile {t} barrier {bid}: " + " ".join(f"{c - min(arr):6d}" for c in arr))
