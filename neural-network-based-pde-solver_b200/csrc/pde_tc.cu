@@ -422,6 +422,25 @@ __device__ __forceinline__ float stream_load(const float* p, uint64_t pol) {
     return *p;
   }
 }
+// the same under a predicate (0 when it is false).  One asm block, so that the register is written by the predicated
+// load itself: a select after the load would make the warp wait for the DRAM round trip right where it was issued.
+__device__ __forceinline__ float stream_load_if(const float* p, uint64_t pol, bool pred) {
+  if constexpr (STASH_HINT) {
+    float v;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %3, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t"
+        "@p ld.global.L2::cache_hint.f32 %0, [%1], %2;\n\t"
+        "}"
+        : "=f"(v)
+        : "l"(p), "l"(pol), "r"((int)pred));
+    return v;
+  } else {
+    return pred ? *p : 0.f;
+  }
+}
 // 128-byte line at p (128-byte aligned) will not be read again before it is rewritten: drop it from L2
 __device__ __forceinline__ void stash_discard(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
 __device__ __forceinline__ void stsm_x2(uint32_t addr, uint32_t r0, uint32_t r1) {
@@ -507,6 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
   uint64_t* bar_own = bar_chunk + 6;   // issuer-private: "everything I issued so far has completed"
   uint64_t* bar_wt = bar_chunk + 7;    // bulk copy of a W tile pair has landed (non-resident W only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_chunk + 8);
+  int* sTileEnd = reinterpret_cast<int*>(bar_chunk + 14);   // the epilogue's loop bound (see there)
   uint64_t* bar_fix = bar_chunk + 9;   // 8 arrivals, epilogue -> issuer: chunk 0 of both operand sets is in place (shadow builds)
   float* sMx = reinterpret_cast<float*>(bar_chunk + 10);   // per-tile maximum cotangent of warps 0 and 1
 
@@ -782,7 +802,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           ph_chunk ^= 1;
           if (elect_one()) {
             const uint32_t d = tm + (16u << 16) + COL_SMALL;
-            const uint32_t kXTK = kXT0 + (((tile - tile_begin) & 1) << 7);   // this tile's x^T buffer (2048 B apart)
+            const uint32_t kXTK = kXT0 + ((tile & 1) << 7);   // this tile's x^T buffer (2048 B apart)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               mma_k(d, kT2M + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
@@ -978,30 +998,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       for (int k = 0; k < XR; ++k) {
         const int i = tid + k * NEPI * 32;
         const long long gp = (long long)tile * TP + i / D;
-        xnext[k] = (i < TP * D && gp < a.n) ? stream_load(a.X + gp * D + (i % D), pol_stream) : 0.f;
+        xnext[k] = stream_load_if(a.X + gp * D + (i % D), pol_stream, i < TP * D && gp < a.n);
       }
     };
     if (tile_begin < tile_end) load_x(tile_begin);
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    // The epilogue is at its register limit and ptxas would keep the loop bound in local memory, whose reload misses L1
+    // behind the stash traffic (~1 k cycles per tile): it is kept in shared memory instead.
+    if (tid == 0) *sTileEnd = tile_end;
+    named_sync(1, NEPI * 32);
+    auto tile_end_s = [&]() {
+      int v;
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(sTileEnd)));
+      return v;
+    };
+    for (int tile = tile_begin; tile < tile_end_s(); ++tile) {
       const long long base = (long long)tile * TP;
       TS(1);
       TSW(1);
       // The previous tile's first-layer MMAs may still be running: they read the adjoint set, the E tiles and the
       // OTHER x^T buffer, none of which this tile's forward sweep writes.  They are waited for in the last forward
       // layer, where their accumulators are added to the running sums.
-      const uint32_t sXTb = sXT + (((tile - tile_begin) & 1) << 11);
+      const uint32_t sXTb = sXT + ((tile & 1) << 11);
       named_sync(1, NEPI * 32);   // everyone is done with sX / sNb / sRed of the previous tile
+      TS(3);
 #pragma unroll
       for (int k = 0; k < XR; ++k)
         if (tid + k * NEPI * 32 < TP * D) sX[tid + k * NEPI * 32] = xnext[k];
       named_sync(1, NEPI * 32);
+      TS(4);
       // the next tile's coordinates and this tile's coefficients are fetched now and used much later
-      if (tile + 1 < tile_end) load_x(tile + 1);
-      float fv = 0.f, bt = a.beta_const;
-      if (tid < TP && base + tid < a.n) {
-        if (a.f) fv = stream_load(a.f + base + tid, pol_stream);
-        if (a.beta) bt = stream_load(a.beta + base + tid, pol_stream);
-      }
+      if (tile + 1 < tile_end_s()) load_x(tile + 1);
+      const bool in_tile = tid < TP && base + tid < a.n;
+      const float fv = stream_load_if(a.f + base + tid, pol_stream, in_tile && a.f != nullptr);
+      const float bt_raw = stream_load_if(a.beta + base + tid, pol_stream, in_tile && a.beta != nullptr);
       if (do_bwd) {
         for (int i = tid; i < D * 32; i += NEPI * 32) {
           const int j = i / 32, pp = 2 * (i % 32);   // row j of X^T, points pp, pp+1
@@ -1013,6 +1042,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         }
       }
 
+      TS(5);
       float outacc[NR][C];
 #pragma unroll
       for (int r = 0; r < NR; ++r)
@@ -1222,7 +1252,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         if (!programmed) {
           if constexpr (!SPLIT) {
             if (gp < a.n) {
-              program_point_lap<D, ORDER>(a, sNb + tid * C, sWL + 65, fv, bt, nj, qs, gE);
+              program_point_lap<D, ORDER>(a, sNb + tid * C, sWL + 65, fv, a.beta ? bt_raw : a.beta_const, nj, qs, gE);
             } else {
 #pragma unroll
               for (int c = 0; c < C; ++c) nj[c] = 0.f;

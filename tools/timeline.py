@@ -24,7 +24,7 @@ for line in open(out):
         wev.setdefault(int(w) - 10, []).append((int(i), int(c)))
     else:
         ev[int(w)].append((int(i), int(c)))
-names = {1: "tile start", 2: "program done"}
+names = {1: "tile start", 2: "program done", 3: "  after barrier 1", 4: "  X in smem, after barrier 2", 5: "  x^T written, loads issued"}
 for k in range(5):
     names[10 + k] = f"F{k} enter"; names[20 + k] = f"F{k} D ready"; names[30 + k] = f"B{k} enter"; names[40 + k] = f"B{k} Ab ready"
     names[50 + k] = f"B{k} want sets"; names[60 + k] = f"B{k} sets free"
