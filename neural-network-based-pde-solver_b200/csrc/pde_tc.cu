@@ -62,6 +62,9 @@ constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp 
 #ifndef PDE_TC_SHADOW
 #define PDE_TC_SHADOW 2         // chunk-0 shadow of the adjoint operand set (see SmemMap); 1: rebuilt A chunk 0 in a fifth pass, 2: parked in TMEM
 #endif
+#ifndef PDE_TC_PARKQ
+#define PDE_TC_PARKQ 1          // six-channel variants: the residual stage's running sums live in TMEM (see PARK_Q)
+#endif
 #define PDE_TC_STR2(x) #x
 #define PDE_TC_STR(x) PDE_TC_STR2(x)
 #if PDE_TC_NEPI == 16
@@ -69,7 +72,9 @@ constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp 
 #define PDE_TC_ISS_REGS 64
 #else
 #define PDE_TC_EPI_REGS 208
-#define PDE_TC_ISS_REGS 80
+#ifndef PDE_TC_ISS_REGS
+#define PDE_TC_ISS_REGS 88      // 256 x 208 + 128 x 88 = the 384 x 168 registers the CTA launches with
+#endif
 #endif
 using StashV = std::conditional<RS == 1, float4, float2>::type;   // one stashed value of a thread's NE elements
 constexpr int MAXC = 6;       // jet channels the TMEM / smem budget covers
@@ -416,7 +421,7 @@ __device__ __forceinline__ float2 stash_load(const float2* p, uint64_t pol) {
 __device__ __forceinline__ float stream_load(const float* p, uint64_t pol) {
   if constexpr (STASH_HINT) {
     float v;
-    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
     return v;
   } else {
     return *p;
@@ -432,7 +437,7 @@ __device__ __forceinline__ float stream_load_if(const float* p, uint64_t pol, bo
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %3, 0;\n\t"
         "mov.f32 %0, 0f00000000;\n\t"
-        "@p ld.global.L2::cache_hint.f32 %0, [%1], %2;\n\t"
+        "@p ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;\n\t"
         "}"
         : "=f"(v)
         : "l"(p), "l"(pol), "r"((int)pred));
@@ -868,6 +873,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 
     double qs[4] = {0.0, 0.0, 0.0, 0.0};
     double gE = 0.0;
+    // Six-channel variants are over the register budget and ptxas would keep these running sums (used once per tile, by
+    // the residual stage of warps 0 and 1) in local memory, whose reloads miss L1 behind the stash traffic.  They are kept
+    // in the last free TMEM columns instead (lane half 1 of the small accumulators' slot, columns 32..47).
+    constexpr bool PARK_Q = (PDE_TC_PARKQ != 0) && (C == 6) && (NEPI == 8);
+    const uint32_t qpark = taddr_of(tmem, 32 * q + 16, COL_SMALL + 32);
+    auto q_load = [&](double (&t)[4], double& g) {
+      uint32_t w0[4], w1[4];
+      tmem_ld_16x256b_u32(qpark, w0);
+      tmem_ld_16x256b_u32(qpark + 8, w1);
+      tmem_ld_wait();
+      t[0] = __hiloint2double((int)w0[1], (int)w0[0]);
+      t[1] = __hiloint2double((int)w0[3], (int)w0[2]);
+      t[2] = t[3] = 0.0;
+      g = __hiloint2double((int)w1[1], (int)w1[0]);
+    };
+    auto q_store = [&](const double (&t)[4], const double g) {
+      const uint32_t w0[4] = {(uint32_t)__double2loint(t[0]), (uint32_t)__double2hiint(t[0]), (uint32_t)__double2loint(t[1]), (uint32_t)__double2hiint(t[1])};
+      const uint32_t w1[4] = {(uint32_t)__double2loint(g), (uint32_t)__double2hiint(g), 0u, 0u};
+      tmem_st_16x256b_u32(qpark, w0);
+      tmem_st_16x256b_u32(qpark + 8, w1);
+      tmem_st_wait();
+    };
+    if constexpr (PARK_Q) {
+      if (tid < TP) q_store(qs, gE);
+    }
     float gwl[4][2];   // output-layer weight gradient partials of this thread's columns
 #pragma unroll
     for (int j = 0; j < 4; ++j) gwl[j][0] = gwl[j][1] = 0.f;
@@ -1250,7 +1280,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           }
         }
         if (!programmed) {
-          if constexpr (!SPLIT) {
+          if constexpr (!SPLIT && PARK_Q) {
+            double tq[4], tg;
+            q_load(tq, tg);
+            if (gp < a.n) {
+              program_point_lap<D, ORDER>(a, sNb + tid * C, sWL + 65, fv, a.beta ? bt_raw : a.beta_const, nj, tq, tg);
+            } else {
+#pragma unroll
+              for (int c = 0; c < C; ++c) nj[c] = 0.f;
+            }
+            q_store(tq, tg);
+          } else if constexpr (!SPLIT) {
             if (gp < a.n) {
               program_point_lap<D, ORDER>(a, sNb + tid * C, sWL + 65, fv, a.beta ? bt_raw : a.beta_const, nj, qs, gE);
             } else {
@@ -1279,8 +1319,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             mx = fmaxf(mx, fabsf(nj[c]));
             sNb[tid * C + c] = nj[c];
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          // non-negative floats order like their bit patterns: one REDUX instead of a five-step shuffle tree
+          mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
           if (lane == 0) sMx[warp] = mx;
         }
         TSW(3);
@@ -1723,6 +1763,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     {
       double* dred = reinterpret_cast<double*>(sm + SM::off_T1);   // 64 x 5 doubles
       if (tid < TP) {
+        if constexpr (PARK_Q) q_load(qs, gE);
 #pragma unroll
         for (int k = 0; k < 4; ++k) dred[tid * 5 + k] = qs[k];
         dred[tid * 5 + 4] = gE;
