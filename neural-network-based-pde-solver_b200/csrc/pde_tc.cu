@@ -53,6 +53,9 @@ constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp 
 #ifndef PDE_TC_STASH_EARLY
 #define PDE_TC_STASH_EARLY 1    // forward: stash stores at the top of the chunk instead of after its proxy fence
 #endif
+#ifndef PDE_TC_LD_EARLY
+#define PDE_TC_LD_EARLY 1       // forward: next chunk's accumulators fetched before this chunk's operand stores (needs STASH_EARLY)
+#endif
 #ifndef PDE_TC_F32X2
 #define PDE_TC_F32X2 1          // sin/cos polynomials in packed fp32 pairs (FFMA2): half the issue slots
 #endif
@@ -1200,6 +1203,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               if constexpr (LAP) av[1 + ND][e] = fmaf(s1, z[1 + ND][e], s2 * S);
             }
           }
+#if PDE_TC_LD_EARLY
+          if (!L0 && j < 3) {
+            // z has been consumed by the chain rule: the accumulators of the next chunk are fetched under this
+            // chunk's operand stores and proxy fence
+#pragma unroll
+            for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), zr[c]);
+          }
+#endif
           // Operand tile first: its fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) would otherwise also wait
           // for the stash stores below to be acknowledged by L2.
           if constexpr (!LAST) {
@@ -1226,11 +1237,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             }
           }
 #endif
+#if !PDE_TC_LD_EARLY
           if (!L0 && j < 3) {
             // z has been consumed: fetch the accumulators of the next chunk now
 #pragma unroll
             for (int c = 0; c < C; ++c) tmem_ld_16x256b(zsrc + ((16 * (c & 1)) << 16) + 64 * (c >> 1) + 16 * (j + 1), zr[c]);
           }
+#endif
         }
         if constexpr (!L0) reg ^= 1;
       };
