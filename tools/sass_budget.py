@@ -57,8 +57,8 @@ L_issuer, L_epi = find("if (warp >= NEPI) {"), find("// epilogue warps")
 L_flush, L_loadx = find("auto flush_grads"), find("auto load_x")
 L_fwd, L_out = find("auto fwd_layer"), find("// ================= output layer + envelope")
 L_bwd, L_res = find("auto bwd_layer"), find("// ================= per-CTA results")
-L_refill = find("if constexpr (REFILL) {", L_bwd + 20)
-L_refill_end = find("if (j == 0 && w_pending) {", L_refill)
+L_refill = find("auto refill = [&]", L_bwd)   # the rebuild of A_{l-1} from its stash
+L_refill_end = find("        };", L_refill)
 core = open("neural-network-based-pde-solver_b200/csrc/pde_tc_core.cuh").read().splitlines()
 L_split = next(i + 1 for i, l in enumerate(core) if "void split2" in l)
 L_sincos1, L_pk = find("void sincos_cw("), find("typedef unsigned long long f32x2;")
