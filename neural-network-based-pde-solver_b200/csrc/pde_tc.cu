@@ -683,6 +683,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       for (int tile = tile_begin; tile < tile_end; ++tile) {
         // ---- forward GEMMs of layers 1..n_h-1, K step j as soon as chunk j of A_{l-1} is there
         for (int l = 1; l < n_h; ++l) {
+          // fresh copies of the descriptor bases: without them ptxas precomputes every (base + tile offset) of the unrolled
+          // issue loops outside the tile loop, ~40 values for the small-C variants, and reloads them from local memory
+          // in front of every K step (the 5- and 6-channel variants keep them in registers and are faster left alone)
+          uint32_t kT1K_ = kT1K, kT1M_ = kT1M, kT2K_ = kT2K, kT2M_ = kT2M, kXT0_ = kXT0, kETK_ = kETK, kZ0_ = kZ0;
+          if constexpr (C <= 4) asm volatile("" : "+r"(kT1K_), "+r"(kT1M_), "+r"(kT2K_), "+r"(kT2M_), "+r"(kXT0_), "+r"(kETK_), "+r"(kZ0_));
           const uint32_t kW = (w_addr(l) >> 4) | DESC_K_LBO;
           const uint32_t dbase = tm + COL_R0 + 192 * reg;
           need_w(l);
@@ -697,7 +702,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
                 const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
-                const uint32_t ah = kT1K + (2 * c) * TD + 2 * j, al = ah + TD;
+                const uint32_t ah = kT1K_ + (2 * c) * TD + 2 * j, al = ah + TD;
                 mma_k(d, ah, DESC_HI, kW + 2 * j, DESC_HI, ID_FWD, j > 0 ? 1u : 0u);
                 mma_k(d, al, DESC_HI, kW + 2 * j, DESC_HI, ID_FWD, 1u);
                 mma_k(d, ah, DESC_HI, kW + TD + 2 * j, DESC_HI, ID_FWD, 1u);
@@ -713,6 +718,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         if (!do_bwd) continue;
         // ---- reverse sweep
         for (int l = n_h - 1; l >= 1; --l) {
+          // fresh copies of the descriptor bases: without them ptxas precomputes every (base + tile offset) of the unrolled
+          // issue loops outside the tile loop, ~40 values for the small-C variants, and reloads them from local memory
+          // in front of every K step (the 5- and 6-channel variants keep them in registers and are faster left alone)
+          uint32_t kT1K_ = kT1K, kT1M_ = kT1M, kT2K_ = kT2K, kT2M_ = kT2M, kXT0_ = kXT0, kETK_ = kETK, kZ0_ = kZ0;
+          if constexpr (C <= 4) asm volatile("" : "+r"(kT1K_), "+r"(kT1M_), "+r"(kT2K_), "+r"(kT2M_), "+r"(kXT0_), "+r"(kETK_), "+r"(kZ0_));
           const uint32_t kW = (w_addr(l) >> 4) | DESC_MN_LBO;
           const uint32_t dbase = tm + COL_R0 + 192 * reg;
           need_w(l);
@@ -729,7 +739,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                   const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
-                  const uint32_t zh = kZ0 + (2 * c) * (2048 >> 4), zl = zh + (2048 >> 4);
+                  const uint32_t zh = kZ0_ + (2 * c) * (2048 >> 4), zl = zh + (2048 >> 4);
                   mma_k(d, zh, DESC_HI_Z0, kW, DESC_HI, ID_DG, 0u);
                   mma_k(d, zl, DESC_HI_Z0, kW, DESC_HI, ID_DG, 1u);
                   mma_k(d, zh, DESC_HI_Z0, kW + TD, DESC_HI, ID_DG, 1u);
@@ -739,7 +749,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
                 const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
-                const uint32_t zh = kT2K + (2 * c) * TD + 2 * j, zl = zh + TD;
+                const uint32_t zh = kT2K_ + (2 * c) * TD + 2 * j, zl = zh + TD;
                 mma_k(d, zh, DESC_HI, kW + 128 * j, DESC_HI, ID_DG, j > 0 ? 1u : 0u);
                 mma_k(d, zl, DESC_HI, kW + 128 * j, DESC_HI, ID_DG, 1u);
                 mma_k(d, zh, DESC_HI, kW + TD + 128 * j, DESC_HI, ID_DG, 1u);
@@ -772,8 +782,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int c = 0; c < C; ++c) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t zh = kT2M + (2 * c) * TD + 128 * ks, zl = zh + TD;
-                const uint32_t ah = kT1M + (2 * c) * TD + 128 * ks, al = ah + TD;
+                const uint32_t zh = kT2M_ + (2 * c) * TD + 128 * ks, zl = zh + TD;
+                const uint32_t ah = kT1M_ + (2 * c) * TD + 128 * ks, al = ah + TD;
                 mma_k(d, zl, DESC_HI, ah, DESC_HI, ID_WG, (c == 0 && ks == 0) ? 0u : 1u);
                 mma_k(d, zh, DESC_HI, al, DESC_HI, ID_WG, 1u);
               }
@@ -782,13 +792,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int c = 0; c < C; ++c) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M + (2 * c) * TD + 128 * ks, DESC_HI, kT1M + (2 * c) * TD + 128 * ks, DESC_HI, ID_WG, 1u);
+                mma_k(d, kT2M_ + (2 * c) * TD + 128 * ks, DESC_HI, kT1M_ + (2 * c) * TD + 128 * ks, DESC_HI, ID_WG, 1u);
             }
             const uint32_t db = tm + (16u << 16) + COL_SMALL + 8 * l;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M + TD + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
+            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M_ + TD + 128 * ks, DESC_HI, kETK_ + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M + 128 * ks, DESC_HI, kETK + 2 * ks, DESC_HI, ID_SM, 1u);
+            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M_ + 128 * ks, DESC_HI, kETK_ + 2 * ks, DESC_HI, ID_SM, 1u);
             mma_commit(bar_w);
           }
           __syncwarp();
@@ -800,6 +810,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         }
         // ---- first layer: [gW0 | gb0] += Zb_{0,0}^T [x | 1] + sum_i Zb_{0,i}^T e_i
         {
+          // fresh copies of the descriptor bases: without them ptxas precomputes every (base + tile offset) of the unrolled
+          // issue loops outside the tile loop, ~40 values for the small-C variants, and reloads them from local memory
+          // in front of every K step (the 5- and 6-channel variants keep them in registers and are faster left alone)
+          uint32_t kT1K_ = kT1K, kT1M_ = kT1M, kT2K_ = kT2K, kT2M_ = kT2M, kXT0_ = kXT0, kETK_ = kETK, kZ0_ = kZ0;
+          if constexpr (C <= 4) asm volatile("" : "+r"(kT1K_), "+r"(kT1M_), "+r"(kT2K_), "+r"(kT2M_), "+r"(kXT0_), "+r"(kETK_), "+r"(kZ0_));
 #pragma unroll
           for (int j = 0; j < 4; ++j) mbar_wait(&bar_chunk[j], ph_chunk);
           if (SHADOW_TAIL) {
@@ -810,25 +825,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           ph_chunk ^= 1;
           if (elect_one()) {
             const uint32_t d = tm + (16u << 16) + COL_SMALL;
-            const uint32_t kXTK = kXT0 + ((tile & 1) << 7);   // this tile's x^T buffer (2048 B apart)
+            const uint32_t kXTK = kXT0_ + ((tile & 1) << 7);   // this tile's x^T buffer (2048 B apart)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              mma_k(d, kT2M + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
-              mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 64 + 2 * ks, DESC_HI, ID_SM, 1u);
+              mma_k(d, kT2M_ + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
+              mma_k(d, kT2M_ + 128 * ks, DESC_HI, kXTK + 64 + 2 * ks, DESC_HI, ID_SM, 1u);
             }
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M + (2 * (1 + i) + 1) * TD + 128 * ks, DESC_HI, kETK + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);
+                mma_k(d, kT2M_ + (2 * (1 + i) + 1) * TD + 128 * ks, DESC_HI, kETK_ + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);
             }
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_k(d, kT2M + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
+            for (int ks = 0; ks < 4; ++ks) mma_k(d, kT2M_ + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);   // E tile of direction dir0 + i: column dir0 + i of gW0
+                mma_k(d, kT2M_ + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK_ + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);   // E tile of direction dir0 + i: column dir0 + i of gW0
             }
             mma_commit(bar_w);
           }
@@ -1913,7 +1928,7 @@ static cudaError_t launch_one(const TcPlan& p, const TcArgs& a, cudaStream_t st)
 template <int ACT>
 static cudaError_t launch_act(const TcPlan& p, const TcArgs& a, cudaStream_t st) {
   if (p.ndir != p.D) {   // dimension-split passes of the 5-D PINN step
-#ifndef PDE_TC_ONLY_CFG2
+#if !defined(PDE_TC_ONLY_CFG2) && !defined(PDE_TC_ONLY_SMALL)
     if (p.D == 5 && p.order == 2 && p.ndir == 3) return launch_one<5, 2, ACT, 3>(p, a, st);
     if (p.D == 5 && p.order == 2 && p.ndir == 2) return launch_one<5, 2, ACT, 2>(p, a, st);
 #endif
@@ -1922,6 +1937,11 @@ static cudaError_t launch_act(const TcPlan& p, const TcArgs& a, cudaStream_t st)
 #ifdef PDE_TC_ONLY_CFG2   // development builds (A/B timing of kernel variants): configs 2 and 3 only
   if (p.D == 3 && p.order == 2 && ACT == 0) return launch_one<3, 2, 0>(p, a, st);
   if (p.D == 5 && p.order == 1 && ACT == 0) return launch_one<5, 1, 0>(p, a, st);
+  return cudaErrorInvalidValue;
+#elif defined(PDE_TC_ONLY_SMALL)   // development builds: the three-channel variants of configs 1 and 4
+  if (p.D == 1 && p.order == 2 && ACT == 0) return launch_one<1, 2, 0>(p, a, st);
+  if (p.D == 2 && p.order == 1 && ACT == 0) return launch_one<2, 1, 0>(p, a, st);
+  if (p.D == 2 && p.order == 2 && ACT == 1) return launch_one<2, 2, 1>(p, a, st);
   return cudaErrorInvalidValue;
 #else
   switch (p.D * 3 + p.order) {
