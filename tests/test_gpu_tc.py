@@ -87,6 +87,9 @@ CASES = [  # d, width, depth, act, program, envelope, N
     (1, 64, 5, "sin", "pinn", "poly", 777), (2, 50, 5, "sin", "pinn", "exp", 2049),
     (1, 50, 4, "tanh", "pinn", "poly", 1000), (2, 50, 5, "sin", "rayleigh", "poly", 1500),
     (4, 33, 3, "tanh", "pinn", "none", 500), (2, 20, 4, "tanh", "drm", "poly", 129), (3, 64, 3, "sin", "mse", "poly", 4097),
+    # five channels at every depth the kernel takes: 2 / 3 / 4 hidden layers = 1 / 2 / 3 GEMM layers behind the two W
+    # slots and the chunk-0 shadow (depth 3: the first layer follows the top layer directly); three tiles per CTA
+    (3, 64, 3, "tanh", "pinn", "poly", 900), (3, 40, 4, "sin", "pinn", "poly", 1300), (3, 64, 5, "sin", "pinn", "poly", 64 * 148 * 3 + 5),
 ]
 
 
@@ -217,6 +220,26 @@ def test_tc_chunk_linearity_full_size_and_determinism():
     assert (g_all - g_mix).abs().max().item() <= TOL * g_all.abs().max().item()
 
 
+def test_tc_loss_only_launch_matches_the_training_launch():
+    """A launch without a reverse sweep (torch.no_grad) over several tiles per CTA returns the loss of the training launch
+    bit for bit: the forward-only path of the two-slot W plan has to bring W_1 back for every tile by itself."""
+    import pde_b200 as pb
+    torch.manual_seed(3)
+    for d, fn in ((3, pb.poisson.pinn_residual_loss), (4, pb.poisson.drm_energy_loss)):   # five jet channels each
+        m = pb.poisson.SolutionNet(d, 64, 5, "FBC").cuda()
+        N = 64 * 148 * 3 + 29
+        X = torch.rand(N, d, device="cuda") * 2
+        f = pb.poisson.rhs_f_for_u_sin(X, 2.0, [1] * d)
+        m.zero_grad()
+        l_train = fn(m, X, f, 2.0)
+        l_train.backward()
+        assert pb.ops.last_kernel_path() == "tcgen05"
+        with torch.no_grad():
+            l_eval = fn(m, X, f, 2.0)
+        assert pb.ops.last_kernel_path() == "tcgen05"
+        assert float(l_eval) == float(l_train.detach())
+
+
 def test_path_selection():
     """Default routing: tensor-core kernel for the shapes it covers above 4096 points, generic kernel
     otherwise (fp64, wide nets); pde_set_kernel_path overrides."""
@@ -265,7 +288,8 @@ def _path_selection(pb):
 
 
 @pytest.mark.parametrize("d,w,depth,order,act,N", [(3, 64, 5, 1, "sin", 777), (2, 50, 4, 1, "tanh", 4099), (1, 20, 3, 1, "tanh", 100),
-                                                 (5, 24, 3, 1, "sin", 64), (2, 64, 4, 0, "sin", 1000), (4, 9, 3, 1, "sin", 333)])
+                                                 (5, 24, 3, 1, "sin", 64), (2, 64, 4, 0, "sin", 1000), (4, 9, 3, 1, "sin", 333),
+                                                 (4, 64, 5, 1, "sin", 64 * 148 * 2 + 100)])   # five channels, forward-only pass over >1 tile per CTA
 def test_tc_jets_forward_backward_vs_numpy_oracle(d, w, depth, order, act, N):
     """pde_jets_forward / pde_jets_backward on the tensor-core kernel (orders 0, 1): jets and the reverse sweep with
     arbitrary cotangents vs oracle/jets_numpy (the same check test_gpu_poisson runs on the generic kernel)."""
