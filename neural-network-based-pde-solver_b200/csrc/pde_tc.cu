@@ -1077,8 +1077,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       // the next tile's coordinates and this tile's coefficients are fetched now and used much later
       if (tile + 1 < tile_end_s()) load_x(tile + 1);
       const bool in_tile = tid < TP && base + tid < a.n;
-      const float fv = stream_load_if(a.f + base + tid, pol_stream, in_tile && a.f != nullptr);
-      const float bt_raw = stream_load_if(a.beta + base + tid, pol_stream, in_tile && a.beta != nullptr);
+      const float fv = stream_load_if(a.f ? a.f + base + tid : nullptr, pol_stream, in_tile && a.f != nullptr);
+      const float bt_raw = stream_load_if(a.beta ? a.beta + base + tid : nullptr, pol_stream, in_tile && a.beta != nullptr);
       if (do_bwd) {
         for (int i = tid; i < D * 32; i += NEPI * 32) {
           const int j = i / 32, pp = 2 * (i % 32);   // row j of X^T, points pp, pp+1
