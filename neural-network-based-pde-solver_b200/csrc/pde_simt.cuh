@@ -731,9 +731,9 @@ __global__ void reduce_kernel(const ReduceArgs<T> a) {
         }
       }
     }
-    // fixed order g = 0, 1, ...; unrolled so that eight of the (independent, L2-latency) loads are in flight
+    // fixed order g = 0, 1, ...; unrolled so that 32 of the (independent, L2-latency) loads are in flight
     double v = 0.0;
-#pragma unroll 8
+#pragma unroll 32
     for (int g = 0; g < a.grid; ++g) v += (double)a.partial[(long long)g * a.PP + src];
     T r = (T)v;
     if (a.accumulate) r += *dst;
