@@ -56,6 +56,9 @@ constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp 
 #ifndef PDE_TC_LD_EARLY
 #define PDE_TC_LD_EARLY 1       // forward: next chunk's accumulators fetched before this chunk's operand stores (needs STASH_EARLY)
 #endif
+#ifndef PDE_TC_PAIR
+#define PDE_TC_PAIR 1           // forward / dgrad GEMMs: two channels per M = 128 instruction (see ch_paired)
+#endif
 #ifndef PDE_TC_F32X2
 #define PDE_TC_F32X2 1          // sin/cos polynomials in packed fp32 pairs (FFMA2): half the issue slots
 #endif
@@ -464,8 +467,26 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) { asm volatile(
 // UMMA descriptors as "constant high word + 14-bit start address (16-byte units) in the low word":
 // K-major / MN-major Tile64 views (LBO 16 / 8192 bytes, SBO 1024 bytes, version 1, SWIZZLE_128B)
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO | version | layout type
+constexpr uint32_t DESC_HI_G2 = (2048u >> 4) | (1u << 14) | (2u << 29);   // MN-major view of a paired channel: 8-row groups 2 KB apart
 constexpr uint32_t DESC_K_LBO = (16u >> 4) << 16;      // low word, next to the start address
 constexpr uint32_t DESC_MN_LBO = (8192u >> 4) << 16;
+// Channel pairs stacked along M (PDE_TC_PAIR).  A tcgen05.mma whose operands both come from shared memory costs what its A
+// tile costs to read, and an M = 128 instruction (52 cycles) is cheaper than two M = 64 ones (2 x 39): channels 2p and 2p+1
+// of an operand set share a pair of 16 KB blocks (hi, lo) with their 8-row groups interleaved (channel c & 1 of point
+// group g at row group 2g + (c & 1)), so that one M = 128 K-major descriptor covers both in the forward and dgrad GEMMs;
+// the accumulator rows land in TMEM exactly where the two M = 64 accumulators used to be interleaved by hand, only with
+// the roles of (lane half, row half) swapped (pick_ch).  An odd last channel keeps the plain (hi tile, lo tile) layout.
+// In the MN-major views (wgrad, first layer, biases) a paired channel simply has its row groups 2 KB apart.
+__host__ __device__ constexpr bool ch_paired(int c, int C) { return PDE_TC_PAIR && ((c | 1) < C); }
+__host__ __device__ constexpr uint32_t ch_base(int c, int C) {   // bytes from the set's start to channel c's first row group (hi part)
+  return ch_paired(c, C) ? (uint32_t)(c >> 1) * 4u * TILE_BYTES + (uint32_t)(c & 1) * 1024u : (uint32_t)c * 2u * TILE_BYTES;
+}
+__host__ __device__ constexpr uint32_t ch_lo(int c, int C) { return ch_paired(c, C) ? 2u * TILE_BYTES : (uint32_t)TILE_BYTES; }   // hi -> lo part
+__host__ __device__ constexpr uint32_t ch_kstep_mn(int c, int C) { return ch_paired(c, C) ? 4096u : 2048u; }   // 16 points in the MN-major view
+__host__ __device__ constexpr uint32_t ch_hi_mn(int c, int C) { return ch_paired(c, C) ? DESC_HI_G2 : DESC_HI; }
+// the same for the chunk-0 shadow (2 KB per channel part, row groups 256 bytes)
+__host__ __device__ constexpr uint32_t z0_base_of(int c, int C) { return ch_paired(c, C) ? (uint32_t)(c >> 1) * 8192u + (uint32_t)(c & 1) * 256u : (uint32_t)c * 4096u; }
+__host__ __device__ constexpr uint32_t z0_lo(int c, int C) { return ch_paired(c, C) ? 4096u : 2048u; }
 // one tcgen05.mma from 32-bit descriptor words
 __device__ __forceinline__ void mma_k(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                       uint32_t accumulate) {
@@ -631,6 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 " PDE_TC_STR(PDE_TC_ISS_REGS) ";");
     if (warp == NEPI) {
       constexpr uint32_t ID_FWD = make_idesc(64, 64, 0, 0);   // A K-major, B K-major
+      constexpr uint32_t ID_FWD2 = make_idesc(128, 64, 0, 0), ID_DG2 = make_idesc(128, 64, 0, 1);   // channel pairs
       constexpr uint32_t ID_DG = make_idesc(64, 64, 0, 1);    // A K-major, B MN-major (W viewed as W^T)
       constexpr uint32_t ID_WG = make_idesc(64, 64, 1, 1);    // A, B MN-major (contraction over points)
       constexpr uint32_t ID_SM = make_idesc(64, 8, 1, 0);     // A MN-major, B K-major, N = 8
@@ -701,11 +723,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             if (elect_one()) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
-                const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
-                const uint32_t ah = kT1K_ + (2 * c) * TD + 2 * j, al = ah + TD;
-                mma_k(d, ah, DESC_HI, kW + 2 * j, DESC_HI, ID_FWD, j > 0 ? 1u : 0u);
-                mma_k(d, al, DESC_HI, kW + 2 * j, DESC_HI, ID_FWD, 1u);
-                mma_k(d, ah, DESC_HI, kW + TD + 2 * j, DESC_HI, ID_FWD, 1u);
+                if (ch_paired(c, C) && (c & 1)) continue;   // covered by its partner's M = 128 instructions
+                const uint32_t d = dbase + 64 * (c >> 1);
+                const uint32_t ah = kT1K_ + (ch_base(c, C) >> 4) + 2 * j, al = ah + (ch_lo(c, C) >> 4);
+                const uint32_t id = ch_paired(c, C) ? ID_FWD2 : ID_FWD;
+                mma_k(d, ah, DESC_HI, kW + 2 * j, DESC_HI, id, j > 0 ? 1u : 0u);
+                mma_k(d, al, DESC_HI, kW + 2 * j, DESC_HI, id, 1u);
+                mma_k(d, ah, DESC_HI, kW + TD + 2 * j, DESC_HI, id, 1u);
               }
             }
             __syncwarp();
@@ -738,21 +762,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
               if (elect_one()) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                  const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
-                  const uint32_t zh = kZ0_ + (2 * c) * (2048 >> 4), zl = zh + (2048 >> 4);
-                  mma_k(d, zh, DESC_HI_Z0, kW, DESC_HI, ID_DG, 0u);
-                  mma_k(d, zl, DESC_HI_Z0, kW, DESC_HI, ID_DG, 1u);
-                  mma_k(d, zh, DESC_HI_Z0, kW + TD, DESC_HI, ID_DG, 1u);
+                  if (ch_paired(c, C) && (c & 1)) continue;
+                  const uint32_t d = dbase + 64 * (c >> 1);
+                  const uint32_t zh = kZ0_ + (z0_base_of(c, C) >> 4), zl = zh + (z0_lo(c, C) >> 4);
+                  const uint32_t id = ch_paired(c, C) ? ID_DG2 : ID_DG;
+                  mma_k(d, zh, DESC_HI_Z0, kW, DESC_HI, id, 0u);
+                  mma_k(d, zl, DESC_HI_Z0, kW, DESC_HI, id, 1u);
+                  mma_k(d, zh, DESC_HI_Z0, kW + TD, DESC_HI, id, 1u);
                 }
               }
             } else if (elect_one()) {
 #pragma unroll
               for (int c = 0; c < C; ++c) {
-                const uint32_t d = dbase + ((16 * (c & 1)) << 16) + 64 * (c >> 1);
-                const uint32_t zh = kT2K_ + (2 * c) * TD + 2 * j, zl = zh + TD;
-                mma_k(d, zh, DESC_HI, kW + 128 * j, DESC_HI, ID_DG, j > 0 ? 1u : 0u);
-                mma_k(d, zl, DESC_HI, kW + 128 * j, DESC_HI, ID_DG, 1u);
-                mma_k(d, zh, DESC_HI, kW + TD + 128 * j, DESC_HI, ID_DG, 1u);
+                if (ch_paired(c, C) && (c & 1)) continue;
+                const uint32_t d = dbase + 64 * (c >> 1);
+                const uint32_t zh = kT2K_ + (ch_base(c, C) >> 4) + 2 * j, zl = zh + (ch_lo(c, C) >> 4);
+                const uint32_t id = ch_paired(c, C) ? ID_DG2 : ID_DG;
+                mma_k(d, zh, DESC_HI, kW + 128 * j, DESC_HI, id, j > 0 ? 1u : 0u);
+                mma_k(d, zl, DESC_HI, kW + 128 * j, DESC_HI, id, 1u);
+                mma_k(d, zh, DESC_HI, kW + TD + 128 * j, DESC_HI, id, 1u);
               }
             }
             __syncwarp();
@@ -782,23 +810,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             for (int c = 0; c < C; ++c) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t zh = kT2M_ + (2 * c) * TD + 128 * ks, zl = zh + TD;
-                const uint32_t ah = kT1M_ + (2 * c) * TD + 128 * ks, al = ah + TD;
-                mma_k(d, zl, DESC_HI, ah, DESC_HI, ID_WG, (c == 0 && ks == 0) ? 0u : 1u);
-                mma_k(d, zh, DESC_HI, al, DESC_HI, ID_WG, 1u);
+                const uint32_t zh = kT2M_ + ((ch_base(c, C) + ks * ch_kstep_mn(c, C)) >> 4), zl = zh + (ch_lo(c, C) >> 4);
+                const uint32_t ah = kT1M_ + ((ch_base(c, C) + ks * ch_kstep_mn(c, C)) >> 4), al = ah + (ch_lo(c, C) >> 4);
+                mma_k(d, zl, ch_hi_mn(c, C), ah, ch_hi_mn(c, C), ID_WG, (c == 0 && ks == 0) ? 0u : 1u);
+                mma_k(d, zh, ch_hi_mn(c, C), al, ch_hi_mn(c, C), ID_WG, 1u);
               }
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M_ + (2 * c) * TD + 128 * ks, DESC_HI, kT1M_ + (2 * c) * TD + 128 * ks, DESC_HI, ID_WG, 1u);
+                mma_k(d, kT2M_ + ((ch_base(c, C) + ks * ch_kstep_mn(c, C)) >> 4), ch_hi_mn(c, C),
+                      kT1M_ + ((ch_base(c, C) + ks * ch_kstep_mn(c, C)) >> 4), ch_hi_mn(c, C), ID_WG, 1u);
             }
             const uint32_t db = tm + (16u << 16) + COL_SMALL + 8 * l;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M_ + TD + 128 * ks, DESC_HI, kETK_ + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
+            for (int ks = 0; ks < 4; ++ks)
+              mma_k(db, kT2M_ + ((ch_lo(0, C) + ks * ch_kstep_mn(0, C)) >> 4), ch_hi_mn(0, C), kETK_ + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M_ + 128 * ks, DESC_HI, kETK_ + 2 * ks, DESC_HI, ID_SM, 1u);
+            for (int ks = 0; ks < 4; ++ks) mma_k(db, kT2M_ + ((ks * ch_kstep_mn(0, C)) >> 4), ch_hi_mn(0, C), kETK_ + 2 * ks, DESC_HI, ID_SM, 1u);
             mma_commit(bar_w);
           }
           __syncwarp();
@@ -828,22 +858,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             const uint32_t kXTK = kXT0_ + ((tile & 1) << 7);   // this tile's x^T buffer (2048 B apart)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              mma_k(d, kT2M_ + TD + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
-              mma_k(d, kT2M_ + 128 * ks, DESC_HI, kXTK + 64 + 2 * ks, DESC_HI, ID_SM, 1u);
+              mma_k(d, kT2M_ + ((ch_lo(0, C) + ks * ch_kstep_mn(0, C)) >> 4), ch_hi_mn(0, C), kXTK + 2 * ks, DESC_HI, ID_SM, ks == 0 ? 0u : 1u);
+              mma_k(d, kT2M_ + ((ks * ch_kstep_mn(0, C)) >> 4), ch_hi_mn(0, C), kXTK + 64 + 2 * ks, DESC_HI, ID_SM, 1u);
             }
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M_ + (2 * (1 + i) + 1) * TD + 128 * ks, DESC_HI, kETK_ + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);
+                mma_k(d, kT2M_ + ((ch_base(1 + i, C) + ch_lo(1 + i, C) + ks * ch_kstep_mn(1 + i, C)) >> 4), ch_hi_mn(1 + i, C),
+                      kETK_ + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);
             }
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma_k(d, kT2M_ + 128 * ks, DESC_HI, kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
+            for (int ks = 0; ks < 4; ++ks) mma_k(d, kT2M_ + ((ks * ch_kstep_mn(0, C)) >> 4), ch_hi_mn(0, C), kXTK + 2 * ks, DESC_HI, ID_SM, 1u);
 #pragma unroll
             for (int i = 0; i < ND; ++i) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                mma_k(d, kT2M_ + (2 * (1 + i)) * TD + 128 * ks, DESC_HI, kETK_ + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);   // E tile of direction dir0 + i: column dir0 + i of gW0
+                mma_k(d, kT2M_ + ((ch_base(1 + i, C) + ks * ch_kstep_mn(1 + i, C)) >> 4), ch_hi_mn(1 + i, C),
+                      kETK_ + 64 * (dir0 + i) + 2 * ks, DESC_HI, ID_SM, 1u);   // E tile of direction dir0 + i: column dir0 + i of gW0
             }
             mma_commit(bar_w);
           }
@@ -878,6 +910,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       } else {
         v[0] = rh ? t[2] : t[0];
         v[1] = rh ? t[3] : t[1];
+      }
+    };
+    // accumulator fragments of channel c from the raw 16x256b loads (one per channel slot, as issued): a paired channel's
+    // two rows come from the two loads of its pair (lane halves = row halves), its columns from word pair c & 1
+    auto pick_ch = [&](const float (&t)[C][4], const int c, float (&v)[NE]) {
+      if (ch_paired(c, C)) {
+        static_assert(!PDE_TC_PAIR || RS == 1, "channel pairs need the 8-warp epilogue");
+        const int p = c & ~1, k = 2 * (c & 1);
+        v[0] = t[p][k]; v[1] = t[p][k + 1]; v[2] = t[p + 1][k]; v[3] = t[p + 1][k + 1];
+      } else {
+        pick(t[c], v);
       }
     };
     uint64_t pol_stash = 0, pol_stream = 0;
@@ -935,12 +978,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
         }
       }
     };
+    // paired channels: the lo part is a pair block (two tiles) further, the 8-row groups are 2 KB apart
+    const uint32_t pair_extra = (uint32_t)(sm_tile * TILE_BYTES) + ((sm_row >> 3) << 10);
     auto put_chunk = [&](uint32_t set, int j, const uint32_t (&pk)[C][NE]) {
       const uint32_t addr = set + sm_base + ((((2 * j + h) ^ sm_r7) & 7) << 4);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        if constexpr (RS == 1) stsm_x4(addr + c * 2 * TILE_BYTES, pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
-        else stsm_x2(addr + c * 2 * TILE_BYTES, pk[c][0], pk[c][1]);
+        const uint32_t ac = addr + ch_base(c, C) + (ch_paired(c, C) ? pair_extra : 0u);
+        if constexpr (RS == 1) stsm_x4(ac, pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+        else stsm_x2(ac, pk[c][0], pk[c][1]);
       }
     };
     // chunk 0 of the adjoints into the shadow (unswizzled: 8-row group g at 256 g, K half h at +128, row at +16 (row & 7))
@@ -948,7 +994,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     auto put_shadow = [&](const uint32_t (&pk)[C][NE]) {
       if constexpr (RS == 1) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) stsm_x4(z0_base + c * 4096, pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
+        for (int c = 0; c < C; ++c)
+          stsm_x4(z0_base + z0_base_of(c, C) + (ch_paired(c, C) ? (pair_extra >> 2) : 0u), pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
       }
     };
     // ... and from there into the adjoint set proper: every warp moves the 16 rows x 16 bytes per tile it wrote itself
@@ -956,12 +1003,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
       const int t = lane >> 4, row = 16 * q + (lane & 15);
       const uint32_t src = sZ0 + (uint32_t)(t * 2048) + ((row >> 3) << 8) + (h << 7) + ((row & 7) << 4);
       const uint32_t dst = sT2 + (uint32_t)(t * TILE_BYTES) + tile_off(row, h);
+      const uint32_t dextra = (uint32_t)(t * TILE_BYTES) + ((row >> 3) << 10);   // paired channels, as in put_chunk
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         uint32_t v0, v1, v2, v3;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(src + c * 4096) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + c * 2 * TILE_BYTES), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                     : "r"(src + z0_base_of(c, C) + (ch_paired(c, C) ? (dextra >> 2) : 0u)) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + ch_base(c, C) + (ch_paired(c, C) ? dextra : 0u)), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
       }
     };
     const uint32_t park = taddr_of(tmem, 32 * q + 16, COL_R0 + 192 * h + 128);
@@ -1158,7 +1207,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             tmem_ld_wait();
             if (l == 1) TS(310 + j);
 #pragma unroll
-            for (int c = 0; c < C; ++c) pick(zr[c], z[c]);
+            for (int c = 0; c < C; ++c) pick_ch(zr, c, z[c]);
 #pragma unroll
             for (int e = 0; e < NE; ++e) z[0][e] += (e & 1) ? b1v : b0v;
           }
@@ -1508,7 +1557,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           } else {
             tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < C; ++c) pick(abr[c], ab[c]);
+            for (int c = 0; c < C; ++c) pick_ch(abr, c, ab[c]);
           }
           float zb[C][NE];
           {
