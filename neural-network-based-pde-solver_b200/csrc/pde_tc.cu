@@ -14,12 +14,17 @@
 //   forward  Z_c   = A_c   W^T      (M = 64 points, N = 64 units, K = 64 units)
 //   dgrad    Ab_c  = Zb_c  W        (same shape, B operand = the same W tile viewed MN-major)
 //   wgrad    gW   += Zb_c^T A_c     (M = N = 64 units, K = 64 points, both operands MN-major views)
-// are tcgen05.mma kind::f16 instructions with UMMA M = 64 accumulators in TMEM; the sin/tanh chain
-// rule, the bf16 hi/lo split and the swizzled operand-tile stores are the SIMT epilogue, which
-// reads the accumulators with tcgen05.ld.16x256b (thread = 2 points x 2 units, all channels).
+// are tcgen05.mma kind::f16 instructions with accumulators in TMEM (forward / dgrad: two channels stacked along
+// M = 128 per instruction, see ch_paired; wgrad: M = 64); the sin/tanh chain rule, the fp16 hi/lo split and the
+// swizzled operand-tile stores are the SIMT epilogue, which reads the accumulators with tcgen05.ld.16x256b
+// (thread = 2 points x 2 units, all channels).
 // Pre-activation jets needed by the reverse sweep are stashed in an L2-resident per-CTA scratch.
-// Parameter gradients (weights and biases of every layer) accumulate in TMEM across all tiles
-// of the CTA and are written once, as a per-CTA partial vector that reduce_kernel sums in fixed order.
+// Parameter gradients (weights and biases of every layer) accumulate in TMEM over one tile and are added to
+// round-to-nearest fp32 running sums in registers (flush_grads); they are written once, as a per-CTA partial
+// vector that reduce_kernel sums in fixed order.
+// Round-2 additions, each described where it lives: chunk-0 shadow of the adjoint set + TMEM parking (SmemMap,
+// bwd_layer), two W slots with W_2 pinned (w_addr), x^T double buffer, envelope jet ahead of the residual stage
+// (envelope_point), loop bound in shared memory, predicated streaming loads.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
