@@ -482,7 +482,7 @@ constexpr uint32_t DESC_MN_LBO = (8192u >> 4) << 16;
 // the accumulator rows land in TMEM exactly where the two M = 64 accumulators used to be interleaved by hand, only with
 // the roles of (lane half, row half) swapped (pick_ch).  An odd last channel keeps the plain (hi tile, lo tile) layout.
 // In the MN-major views (wgrad, first layer, biases) a paired channel simply has its row groups 2 KB apart.
-__host__ __device__ constexpr bool ch_paired(int c, int C) { return PDE_TC_PAIR && ((c | 1) < C); }
+__host__ __device__ constexpr bool ch_paired(int c, int C) { return PDE_TC_PAIR && RS == 1 && ((c | 1) < C); }   // 8-warp epilogue only
 __host__ __device__ constexpr uint32_t ch_base(int c, int C) {   // bytes from the set's start to channel c's first row group (hi part)
   return ch_paired(c, C) ? (uint32_t)(c >> 1) * 4u * TILE_BYTES + (uint32_t)(c & 1) * 1024u : (uint32_t)c * 2u * TILE_BYTES;
 }
@@ -921,7 +921,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
     // two rows come from the two loads of its pair (lane halves = row halves), its columns from word pair c & 1
     auto pick_ch = [&](const float (&t)[C][4], const int c, float (&v)[NE]) {
       if (ch_paired(c, C)) {
-        static_assert(!PDE_TC_PAIR || RS == 1, "channel pairs need the 8-warp epilogue");
         const int p = c & ~1, k = 2 * (c & 1);
         v[0] = t[p][k]; v[1] = t[p][k + 1]; v[2] = t[p + 1][k]; v[3] = t[p + 1][k + 1];
       } else {
@@ -1697,24 +1696,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
             w_pending = false;
             TS(60 + l);
           }
-          if (SHP0 && j <= 2) {
-            if (j == 0) {
-              put_shadow(zk);
-            } else if (j == 1) {
+          if constexpr (SHP0) {   // (shadow builds have the 8-warp epilogue: NE == 4)
+            if (j <= 2) {
+              if (j == 0) {
+                put_shadow(zk);
+              } else if (j == 1) {
 #pragma unroll
-              for (int c = 0; c < C; ++c) tmem_st_16x256b_u32(park + 8 * c, zk[c]);
-              tmem_st_wait();
-            } else {
-              put_chunk(sT2, 2, zk);
-              uint32_t pk[C][NE];
+                for (int c = 0; c < C; ++c) tmem_st_16x256b_u32(park + 8 * c, zk[c]);
+                tmem_st_wait();
+              } else {
+                put_chunk(sT2, 2, zk);
+                uint32_t pk[C][NE];
 #pragma unroll
-              for (int c = 0; c < C; ++c) tmem_ld_16x256b_u32(park + 8 * c, pk[c]);
-              tmem_ld_wait();
-              put_chunk(sT2, 1, pk);
-              copy_shadow();
-              chunk_done(2);   // publishes chunks 0..2
+                for (int c = 0; c < C; ++c) tmem_ld_16x256b_u32(park + 8 * c, pk[c]);
+                tmem_ld_wait();
+                put_chunk(sT2, 1, pk);
+                copy_shadow();
+                chunk_done(2);   // publishes chunks 0..2
+              }
+              continue;
             }
-            continue;
           }
           if (SH && j == 0) {
             put_shadow(zk);
@@ -1729,7 +1730,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_kernel(const TcArgs a) {
           } else {
             put_chunk(sT2, j, zk);
             if constexpr (REFILL) store_chunk(sT1, j, ap);
-            if (SHP && j == 1) {
+            if constexpr (SHP) if (j == 1) {
               // the sets are free: chunk 0 moves from the shadow / TMEM to its place
               if constexpr (REFILL) {
                 uint32_t pk[C][NE];

@@ -148,12 +148,21 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, float (&v)[8])
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-// 16 lanes x 8 columns, raw words, and the matching store
-__device__ __forceinline__ void tmem_ld_16x256b_u32(uint32_t taddr, uint32_t (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+// 16 lanes x 8 columns, raw words, and the matching store (N = 4 words per thread; other N only exist so that the
+// 16-warp build switch, which never reaches these calls, still compiles)
+template <int N>
+__device__ __forceinline__ void tmem_ld_16x256b_u32(uint32_t taddr, uint32_t (&v)[N]) {
+  if constexpr (N == 4)
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+  else
+    __trap();
 }
-__device__ __forceinline__ void tmem_st_16x256b_u32(uint32_t taddr, const uint32_t (&v)[4]) {
-  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+template <int N>
+__device__ __forceinline__ void tmem_st_16x256b_u32(uint32_t taddr, const uint32_t (&v)[N]) {
+  if constexpr (N == 4)
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+  else
+    __trap();
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
