@@ -561,7 +561,9 @@ def main():
     copy_stream = torch.cuda.Stream(dev)
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
-    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses_read = []
 
     def upload(i):
         s = i % 2
@@ -585,15 +587,25 @@ def main():
             loss = pb.poisson.pinn_residual_loss(model, dX[s], df[s], L_DOM, group=group, n_global=n_global)
             loss.backward()
             freed[s].record(torch.cuda.current_stream())
-            host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()   # the caller reads the loss every step
+            host_loss[s].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ready[s].record(torch.cuda.current_stream())
+            # the caller reads every step's loss, one step late: step i is queued before the host waits for the loss
+            # of step i-1, as a training loop that logs its loss would do, so the GPU does not idle on the read-back
+            if i > 0:
+                loss_ready[1 - s].synchronize()
+                losses_read.append(float(host_loss[1 - s][0]))
+        loss_ready[(k - 1) % 2].synchronize()
+        losses_read.append(float(host_loss[(k - 1) % 2][0]))
 
     e2e_steps(2)
+    losses_read.clear()
     barrier()
     t0 = time.perf_counter()
     e2e_steps(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    if len(losses_read) != args.steps or not all(math.isfinite(v) for v in losses_read):
+        raise RuntimeError(f"end-to-end loop read {len(losses_read)} losses for {args.steps} steps: {losses_read[:4]}")
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -619,7 +631,8 @@ def main():
             "config": cfg, "exchange": exchange, "kernel_path": kernel_path,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "how": "pinned host X,f -> device on a copy stream one step ahead; loss .item()-style readback every step"},
+                    "how": "pinned host X,f -> device on a copy stream one step ahead; every step's loss is copied to pinned host memory and read by the host after the next step has been queued (all reads inside the timed region)",
+                    "losses_read": len(losses_read)},
             "gpu_launches": launches,
             "gpu_launches_how": ("pde_launch_count() delta over the timed region (counted at the library's launch sites): per step "
                                  "tc_pack_kernel, tc_kernel<3,2,sin>, reduce_kernel" + (" (with the NVLink exchange in its tail)" if world > 1 else "")
