@@ -365,7 +365,7 @@ def extra_configs(dev, peak_tflops):
         else:
             cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "port", "sample": "oracle/_ref absent: not timed"}
         ops_path = path
-        optc = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+        optc = pb.train.Adam(m.parameters(), lr=1e-3)   # torch.optim.Adam's update in one launch (gradients: views of one flat buffer)
 
         def q_epoch():
             optc.zero_grad(set_to_none=False)
@@ -376,7 +376,7 @@ def extra_configs(dev, peak_tflops):
         entry(f"config 4: QHO_2D 2-D eigenstate PINN {tech}, [2,50,50,50,50,1], 200x200 grid", 40000, ms,
               flop_per_point(4, 50, 5, 2), cpu,
               {"kernel_path": ops_path, "fused_epoch_ms": ep, "fused_epoch_points_per_s": 40000 / ep * 1e3,
-               "fused_epoch": "loss step + torch Adam(capturable) as one replayed CUDA graph (pde_b200.train.GraphedEpoch)"})
+               "fused_epoch": "loss step + pde_b200.train.Adam (one-launch Adam) as one replayed CUDA graph (pde_b200.train.GraphedEpoch)"})
 
     # config 5: IPW_1D_WAN minimax pair, one evaluation of WAN_loss + backward into both networks
     torch.manual_seed(0)
@@ -399,8 +399,8 @@ def extra_configs(dev, peak_tflops):
                "sample": f"the whole 1000-point evaluation ({dt * 1e3:.2f} ms): oracle/_ref/IPW_1D_WAN.py WAN_loss + backward, fp32"}
     else:
         cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "port", "sample": "oracle/_ref absent: not timed"}
-    ouc = torch.optim.Adam(um.parameters(), lr=1e-3, capturable=True)
-    ovc = torch.optim.Adam(vm.parameters(), lr=1e-3, capturable=True)
+    ouc = pb.train.Adam(um.parameters(), lr=1e-3)
+    ovc = pb.train.Adam(vm.parameters(), lr=1e-3)
 
     def wan_epoch():     # IPW_1D_WAN.py:186-208: five critic steps on the frozen solution network, then one solution step
         Ju = pb.frozen_jets(um, x)

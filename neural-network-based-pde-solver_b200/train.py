@@ -108,6 +108,47 @@ class FusedAdam:
                     "pde_adam_step")
 
 
+class Adam:
+    """``torch.optim.Adam(params, lr, betas, eps, weight_decay)`` for reference-style epochs (``zero_grad -> loss ->
+    backward -> step``), at three launches per step instead of torch's ~45: the parameters' ``.grad`` tensors are made
+    views of one flat buffer, so ``zero_grad()`` is one fill, autograd accumulates into the views in place, and
+    ``step()`` is one ``pde_adam_step`` launch over all tensors (same update rule and state as ``FusedAdam``).
+    Nothing synchronises, so it can be captured in a ``GraphedEpoch`` as it is (no ``capturable`` flag needed); the
+    arithmetic is that of torch's default Adam, bias corrections in double (``capturable=True`` keeps its step count in
+    float32 and is ~6e-6 per step away from it)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params]
+        self._opt = FusedAdam(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        p0 = self.params[0]
+        self.flat = torch.zeros(self._opt.n, dtype=p0.dtype, device=p0.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def state(self):
+        return {"exp_avg": self._opt.exp_avg, "exp_avg_sq": self._opt.exp_avg_sq, "step": self._opt.step_count}
+
+    def zero_grad(self, set_to_none=False):
+        """One fill of the flat buffer; ``set_to_none`` is ignored (the views have to stay in place)."""
+        for p, off in zip(self.params, self._offsets()):
+            g = p.grad
+            if g is None or g.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
+                p.grad = self.flat[off:off + p.numel()].view_as(p)   # someone replaced the view (e.g. set_to_none elsewhere)
+        self.flat.zero_()
+
+    def _offsets(self):
+        off = 0
+        for p in self.params:
+            yield off
+            off += p.numel()
+
+    def step(self):
+        self._opt.step(self.flat)
+
+
 class FusedTrainer:
     """The PINN / DRM branch of ``train_poisson_nd`` (Poisson_ND.py:215-241,281-300) with every epoch
     replayed from one CUDA graph: PDE term plus, when their weights are non-zero, the soft Dirichlet
@@ -519,8 +560,9 @@ class GraphedEpoch:
     side of an epoch (Python, autograd bookkeeping, ~20 small launches per loss) disappears on replay;
     this is what makes the latency-bound configurations (1 000 – 40 000 points: IPW / QHO / KH grids,
     BASELINE.json configs 1, 4, 5) run at kernel speed.  Requirements on ``fn``: static input tensors,
-    no ``.item()`` / host read-back inside, optimisers built with ``capturable=True``, gradients
-    allocated before capture (``warmup`` eager epochs on a side stream take care of that).
+    no ``.item()`` / host read-back inside, optimisers built with ``capturable=True`` (or ``pb.train.Adam``, which
+    updates all parameter tensors in one launch), gradients allocated before capture (``warmup`` eager epochs on a
+    side stream take care of that).
 
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
         def epoch():

@@ -178,6 +178,48 @@ def test_wan_frozen_jets_give_identical_losses_and_grads():
         W.WAN_loss(um, vm, x, n, L, u_jets=Ju[:10])
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_train_adam_dropin_matches_torch_adam(graph):
+    """pb.train.Adam (gradients as views of one flat buffer, one pde_adam_step launch per step) follows
+    torch.optim.Adam through a reference-style epoch on the QHO 2-D PINN loss, eagerly and as a replayed CUDA graph."""
+    from pde_b200.schrodinger import qho_2d as Q
+    g1 = torch.linspace(-6.0, 6.0, 40, dtype=torch.float64)
+    xg, yg = torch.meshgrid(g1, g1, indexing="ij")
+    xd, yd = xg.cuda(), yg.cuda()
+    E = Q.Exact_energy(2, 1, 6.0)
+
+    def build(kind):
+        torch.manual_seed(11)
+        m = Q.FCN([2, 24, 24, 24, 1], 2, 1, "FBC").double().cuda()
+        opt = (pb.train.Adam(m.parameters(), lr=2e-3, weight_decay=1e-4) if kind == "fused"
+               else torch.optim.Adam(m.parameters(), lr=2e-3, weight_decay=1e-4))   # (capturable=True keeps its step count, hence
+                                                                                      #  the bias corrections, in float32: 6e-6 off per step)
+
+        def epoch():
+            opt.zero_grad(set_to_none=False)
+            l = Q.PINN_loss(m, xd, yd, E, 6.0)
+            l.backward()
+            opt.step()
+            return l.detach()
+        return m, epoch
+    m_ref, ep_ref = build("torch")
+    for _ in range(7):
+        l_ref = ep_ref()
+    m_new, ep_new = build("fused")
+    if graph:
+        ge = pb.train.GraphedEpoch(ep_new, warmup=3)
+        ge()                       # 3 eager epochs + capture
+        for _ in range(4):
+            l_new = ge()           # 4 replays
+    else:
+        for _ in range(7):
+            l_new = ep_new()
+    torch.cuda.synchronize()
+    assert abs(float(l_new) - float(l_ref)) <= 1e-9 * abs(float(l_ref))
+    for a, b in zip(m_new.parameters(), m_ref.parameters()):
+        assert float((a - b).abs().max()) <= 1e-9 * max(1.0, float(b.abs().max()))
+
+
 def test_graphed_wan_epoch_matches_eager():
     """One epoch of the IPW 1-D WAN loop (5 critic steps + 1 solution step, IPW_1D_WAN.py:186-208) captured as a
     CUDA graph equals the same epoch run eagerly."""
