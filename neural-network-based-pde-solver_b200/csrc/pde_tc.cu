@@ -82,7 +82,9 @@ constexpr int NTHREADS = (NEPI + 4) * 32;   // + one warpgroup whose first warp 
 #define PDE_TC_EPI_REGS 104     // 640 threads launch at 96 registers; setmaxnreg only redistributes those 61 440
 #define PDE_TC_ISS_REGS 64
 #else
+#ifndef PDE_TC_EPI_REGS
 #define PDE_TC_EPI_REGS 208
+#endif
 #ifndef PDE_TC_ISS_REGS
 #define PDE_TC_ISS_REGS 88      // 256 x 208 + 128 x 88 = the 384 x 168 registers the CTA launches with
 #endif
