@@ -365,10 +365,10 @@ def extra_configs(dev, peak_tflops):
         else:
             cpu = {"value": None, "unit": "points/s", "cores": cores, "kind": "port", "sample": "oracle/_ref absent: not timed"}
         ops_path = path
-        optc = pb.train.Adam(m.parameters(), lr=1e-3)   # torch.optim.Adam's update in one launch (gradients: views of one flat buffer)
+        optc = pb.train.Adam(m.parameters(), lr=1e-3)   # torch.optim.Adam's update in one launch, reading the loss operator's flat gradient buffer in place
 
         def q_epoch():
-            optc.zero_grad(set_to_none=False)
+            optc.zero_grad()
             l = Q.PINN_loss(m, xd, yd, E, 6.0); l.backward(); optc.step()
             return l.detach()
         ge = pb.train.GraphedEpoch(q_epoch); ge()
@@ -405,9 +405,9 @@ def extra_configs(dev, peak_tflops):
     def wan_epoch():     # IPW_1D_WAN.py:186-208: five critic steps on the frozen solution network, then one solution step
         Ju = pb.frozen_jets(um, x)
         for _ in range(5):
-            ovc.zero_grad(set_to_none=False)
+            ovc.zero_grad()
             W.WAN_loss(um, vm, x, 2, 2.0, u_jets=Ju)[1].backward(inputs=list(vm.parameters())); ovc.step()
-        ouc.zero_grad(set_to_none=False)
+        ouc.zero_grad()
         t = W.WAN_loss(um, vm, x, 2, 2.0)[0]; t.backward(inputs=list(um.parameters())); ouc.step()
         return t.detach()
     gw = pb.train.GraphedEpoch(wan_epoch); gw()

@@ -398,7 +398,7 @@ class _Residual(torch.autograd.Function):
             ctx.shapes = [p.shape for p in ps]
         else:
             ctx.save_for_backward(X, f, beta, e_dev, *ps)
-        return means.clone()
+        return means     # (a fresh tensor: the division in combine_forward)
 
     @staticmethod
     def backward(ctx, gmeans):
@@ -490,6 +490,15 @@ def residual_means(model, X, spec: ProgramSpec, env: EnvelopeSpec = NO_ENVELOPE,
     return _Residual.apply(net, env, spec, group, n_global, need_grad, X, coef(f), coef(beta), e, *net.params)
 
 
+def residual_mean(model, X, spec: ProgramSpec, env: EnvelopeSpec = NO_ENVELOPE, **kw) -> torch.Tensor:
+    """``residual_means`` of a one-quantity program (PINN residual, Deep Ritz energy, MSE) as a 0-d tensor.  A view:
+    indexing ``means[0]`` costs two launches in backward (select_backward = zero fill + copy), a reshape none."""
+    m = residual_means(model, X, spec, env, **kw)
+    if m.numel() != 1:
+        raise ValueError("residual_mean is for programs with one quantity")
+    return m.reshape(())
+
+
 # ---------------------------------------------------------------------------------------------
 # WAN coupling of two networks
 # ---------------------------------------------------------------------------------------------
@@ -522,7 +531,7 @@ class _WanPoint(torch.autograd.Function):
         e_dev = energy.detach().reshape(1).to(dt) if energy is not None else None
         w.energy = e_dev.data_ptr() if e_dev is not None else None
         w.env_u, w.env_v = env_u.to_c(), env_v.to_c()
-        sums = torch.zeros(5, dtype=dt, device=dev)
+        sums = torch.empty(5, dtype=dt, device=dev)    # all five written by the launch (wan_finish_kernel)
         ws = _workspace(dev, 1 << 20)
         Juc, Jvc = Ju.detach().contiguous(), Jv.detach().contiguous()
         with torch.cuda.device(dev):

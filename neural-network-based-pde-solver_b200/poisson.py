@@ -14,7 +14,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, mlp_jets, residual_means, wan_means, wan_scalar_losses)
+from .ops import (NO_ENVELOPE, EnvelopeSpec, ProgramSpec, WanSpec, mlp_jets, residual_mean, residual_means, wan_means,
+                  wan_scalar_losses)
 
 
 class Sin(nn.Module):
@@ -89,16 +90,14 @@ def _envelope(model, L):
 
 def pinn_residual_loss(model, X_in, f_in, L, *, group=None, n_global=None):
     """mean((-Lap u - f)^2)   (Poisson_ND.py:91-96)."""
-    m = residual_means(model, X_in, ProgramSpec(_lib.PROG_PINN, alpha=-1.0), _envelope(model, L), f=f_in,
-                       group=group, n_global=n_global)
-    return m[0]
+    return residual_mean(model, X_in, ProgramSpec(_lib.PROG_PINN, alpha=-1.0), _envelope(model, L), f=f_in,
+                         group=group, n_global=n_global)
 
 
 def drm_energy_loss(model, X_in, f_in, L, *, group=None, n_global=None):
     """mean(1/2 |grad u|^2 - f u)   (Poisson_ND.py:98-103)."""
-    m = residual_means(model, X_in, ProgramSpec(_lib.PROG_DRM, alpha=0.5), _envelope(model, L), f=f_in,
-                       group=group, n_global=n_global)
-    return m[0]
+    return residual_mean(model, X_in, ProgramSpec(_lib.PROG_DRM, alpha=0.5), _envelope(model, L), f=f_in,
+                         group=group, n_global=n_global)
 
 
 def wan_losses(u_model, v_model, X, f_vals, L, eps=1e-8, v_reg_weight=0.0, *, group=None, n_global=None,
@@ -123,15 +122,15 @@ def boundary_loss_dirichlet(model, L, N_b_per_face, dim, device, *, group=None):
             if group is not None:
                 import torch.distributed as dist
                 n_glob = N_b_per_face * dist.get_world_size(group)
-            losses.append(residual_means(model, X, ProgramSpec(_lib.PROG_MSE), _envelope(model, L), group=group,
-                                         n_global=n_glob)[0])
+            losses.append(residual_mean(model, X, ProgramSpec(_lib.PROG_MSE), _envelope(model, L), group=group,
+                                        n_global=n_glob))
     return sum(losses) / len(losses)
 
 
 def data_loss(model, X_data, u_data, L, *, group=None, n_global=None):
     """mean((u(X_data) - u_data)^2)   (Poisson_ND.py:230-232)."""
-    return residual_means(model, X_data, ProgramSpec(_lib.PROG_MSE), _envelope(model, L), f=u_data, group=group,
-                          n_global=n_global)[0]
+    return residual_mean(model, X_data, ProgramSpec(_lib.PROG_MSE), _envelope(model, L), f=u_data, group=group,
+                         n_global=n_global)
 
 
 def norm_loss(u, mode='nontrivial', eps=1e-8):

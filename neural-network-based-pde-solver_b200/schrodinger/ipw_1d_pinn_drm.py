@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import ProgramSpec, residual_means
+from ..ops import ProgramSpec, residual_mean, residual_means
 from ._common import NO_ENVELOPE, mlp, poly_envelope
 
 
@@ -48,7 +48,7 @@ def _envelope(model):
 def PINN_loss(model, x, n, L):
     """mean((u'' + k^2 u)^2), k^2 = (n pi / L)^2   (IPW_1D_PINN_DRM.py:63-83)."""
     E = (n * np.pi) ** 2 / (2 * L ** 2)
-    return residual_means(model, x, ProgramSpec(_lib.PROG_PINN, alpha=1.0, beta_const=2.0 * E), _envelope(model))[0]
+    return residual_mean(model, x, ProgramSpec(_lib.PROG_PINN, alpha=1.0, beta_const=2.0 * E), _envelope(model))
 
 
 def DRM_loss(model, x):

@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import ProgramSpec, residual_means
+from ..ops import ProgramSpec, residual_mean, residual_means
 from ._common import Sin, mlp, poly_envelope, values
 
 
@@ -56,8 +56,8 @@ def k_squared(nx, ny, L):
 
 def PINN_loss(model, x, y, nx, ny, L=2.0):
     """mean((u_xx + u_yy + k^2 u)^2): the inline residual block of train_pinn_seperate (IPW_2D.py:195-224)."""
-    return residual_means(model, _points(x, y), ProgramSpec(_lib.PROG_PINN, alpha=1.0, beta_const=k_squared(nx, ny, L)),
-                          _envelope(model, L))[0]
+    return residual_mean(model, _points(x, y), ProgramSpec(_lib.PROG_PINN, alpha=1.0, beta_const=k_squared(nx, ny, L)),
+                         _envelope(model, L))
 
 
 def DRM_loss(model, x, y, L=2.0):
@@ -68,8 +68,8 @@ def DRM_loss(model, x, y, L=2.0):
 
 def data_loss(model, X_data, Y_data, u_data, L=2.0):
     """mean((u(X_data, Y_data) - u_data)^2)   (IPW_2D.py:230-232)."""
-    return residual_means(model, _points(X_data, Y_data), ProgramSpec(_lib.PROG_MSE), _envelope(model, L),
-                          f=u_data.detach().reshape(-1))[0]
+    return residual_mean(model, _points(X_data, Y_data), ProgramSpec(_lib.PROG_MSE), _envelope(model, L),
+                         f=u_data.detach().reshape(-1))
 
 
 def orthogonal_loss(model, x, y, nx, ny, L):

@@ -4,7 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import NO_ENVELOPE, ProgramSpec, WanSpec, residual_means, wan_means, wan_scalar_losses
+from ..ops import NO_ENVELOPE, ProgramSpec, WanSpec, residual_mean, residual_means, wan_means, wan_scalar_losses
 from ._common import Sin, mlp, window_envelope
 
 
@@ -99,7 +99,7 @@ def pinn_loss(model, x, alpha, V0, use_avg=True, n_theta=500):
     if getattr(model.u_model, "technique", 'RAW') != 'RAW':
         env = _envelope(model, x.detach().abs().max().item())      # the reference syncs here too (:227)
     Vx = _potential(x, alpha, V0, use_avg, n_theta)
-    return residual_means(model, x, ProgramSpec(_lib.PROG_PINN, alpha=-0.5), env, beta=Vx, energy=model.energy)[0]
+    return residual_mean(model, x, ProgramSpec(_lib.PROG_PINN, alpha=-0.5), env, beta=Vx, energy=model.energy)
 
 
 def drm_loss(model, x, alpha, V0, L, use_avg=True, n_theta=500):

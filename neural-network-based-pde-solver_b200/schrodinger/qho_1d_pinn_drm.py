@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import ProgramSpec, residual_means
+from ..ops import ProgramSpec, residual_mean, residual_means
 from ._common import NO_ENVELOPE, values, window_envelope
 from .qho_2d import hermite_nodes
 
@@ -104,8 +104,8 @@ def _envelope(model):
 def PINN_loss(model, x):
     """mean((-1/2 u'' + V u - E_n u)^2)   (QHO_1D_PINN_DRM.py:161-174)."""
     V = Potential(x.detach())
-    return residual_means(model, x, ProgramSpec(_lib.PROG_PINN, alpha=-0.5, energy_const=Energy(model.num_states)),
-                          _envelope(model), beta=V)[0]
+    return residual_mean(model, x, ProgramSpec(_lib.PROG_PINN, alpha=-0.5, energy_const=Energy(model.num_states)),
+                         _envelope(model), beta=V)
 
 
 def DRM_loss(model, x):
@@ -117,7 +117,7 @@ def DRM_loss(model, x):
 
 def normalization_loss(model, x):
     """(sqrt(sum(u^2) dx) - 1)^2 on a uniform grid (QHO_1D_PINN_DRM.py:187-195)."""
-    m2 = residual_means(model, x, ProgramSpec(_lib.PROG_MSE), _envelope(model))[0]
+    m2 = residual_mean(model, x, ProgramSpec(_lib.PROG_MSE), _envelope(model))
     xd = x.detach()
     dx = (xd[1] - xd[0]).reshape(())
     return (torch.sqrt(m2 * xd.shape[0] * dx) - 1) ** 2

@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..ops import ProgramSpec, WanSpec, residual_means, wan_means, wan_scalar_losses
+from ..ops import ProgramSpec, WanSpec, residual_mean, residual_means, wan_means, wan_scalar_losses
 from ._common import Sin, mlp, window_envelope
 
 OMEGA = math.sqrt(2)
@@ -75,7 +75,7 @@ def PINN_loss(model, x, y, E, L=6.0):
     """mean((-1/2 Lap u + V u - E u)^2): the inline residual block of train_pinn_seperate
     (QHO_2D.py:363-378).  ``E`` may be a float or a trainable scalar tensor (QHO_2D_Energy.py:382-383)."""
     X, V = _points(x, y)
-    return residual_means(model, X, ProgramSpec(_lib.PROG_PINN, alpha=-0.5), _envelope(model, L), beta=V, energy=E)[0]
+    return residual_mean(model, X, ProgramSpec(_lib.PROG_PINN, alpha=-0.5), _envelope(model, L), beta=V, energy=E)
 
 
 def DRM_loss(model, x, y, L=6.0):

@@ -110,43 +110,92 @@ class FusedAdam:
 
 class Adam:
     """``torch.optim.Adam(params, lr, betas, eps, weight_decay)`` for reference-style epochs (``zero_grad -> loss ->
-    backward -> step``), at three launches per step instead of torch's ~45: the parameters' ``.grad`` tensors are made
-    views of one flat buffer, so ``zero_grad()`` is one fill, autograd accumulates into the views in place, and
-    ``step()`` is one ``pde_adam_step`` launch over all tensors (same update rule and state as ``FusedAdam``).
-    Nothing synchronises, so it can be captured in a ``GraphedEpoch`` as it is (no ``capturable`` flag needed); the
-    arithmetic is that of torch's default Adam, bias corrections in double (``capturable=True`` keeps its step count in
-    float32 and is ~6e-6 per step away from it)."""
+    backward -> step``) at two or three launches of bookkeeping per step instead of torch's ~45: ``step()`` is one
+    ``pde_adam_step`` launch over all parameter tensors, fed by one flat gradient vector (same update rule and state as
+    ``FusedAdam``).  Where that vector comes from depends on how the gradients were zeroed:
+
+    * ``zero_grad()`` (``set_to_none=True``, torch's default): no launch.  The drop-in losses hand autograd views of
+      *one* flat gradient buffer (``ops._Residual`` / ``ops._Jets``), which autograd adopts as ``p.grad`` without
+      copying when ``p.grad`` is None; ``step()`` recognises that layout (same storage, consecutive offsets in
+      parameter order) and passes the buffer to the kernel as it is.  A second ``backward()`` accumulates into the
+      adopted views in place, which keeps the layout; several operator terms inside one ``backward()`` are summed per
+      parameter by the autograd engine before they reach ``p.grad`` and are gathered (below).
+    * ``zero_grad(set_to_none=False)``: the ``.grad`` tensors are views of the optimiser's own flat buffer, zeroed by
+      one fill; autograd adds into them (one small launch per parameter tensor).
+
+    Gradients that arrive in any other layout (other operators, a different parameter order, hooks) are gathered into
+    the optimiser's buffer first (one ``torch.cat``; a parameter without gradient counts as zero gradient — torch.optim
+    would skip it).  Nothing synchronises, so an epoch can be captured in a ``GraphedEpoch`` as it is (no ``capturable``
+    flag needed); the arithmetic is that of torch's default Adam, bias corrections in double (``capturable=True`` keeps
+    its step count in float32 and is ~6e-6 per step away from it)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.params = [p for p in params]
         self._opt = FusedAdam(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         p0 = self.params[0]
         self.flat = torch.zeros(self._opt.n, dtype=p0.dtype, device=p0.device)
+        self._off = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self._off.append(off)
             off += p.numel()
+        self.adopted_steps = 0     # steps that took the gradients where autograd left them (no gather, no fill)
+        self.gathered_steps = 0
 
     @property
     def state(self):
         return {"exp_avg": self._opt.exp_avg, "exp_avg_sq": self._opt.exp_avg_sq, "step": self._opt.step_count}
 
-    def zero_grad(self, set_to_none=False):
-        """One fill of the flat buffer; ``set_to_none`` is ignored (the views have to stay in place)."""
-        for p, off in zip(self.params, self._offsets()):
+    def _own_view(self, i):
+        p, off = self.params[i], self._off[i]
+        return self.flat[off:off + p.numel()].view_as(p)
+
+    def zero_grad(self, set_to_none=True):
+        if set_to_none:
+            for p in self.params:
+                p.grad = None
+            return
+        es = self.flat.element_size()
+        for i, p in enumerate(self.params):
             g = p.grad
-            if g is None or g.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
-                p.grad = self.flat[off:off + p.numel()].view_as(p)   # someone replaced the view (e.g. set_to_none elsewhere)
+            if g is None or g.data_ptr() != self.flat.data_ptr() + self._off[i] * es or not g.is_contiguous():
+                p.grad = self._own_view(i)
         self.flat.zero_()
 
-    def _offsets(self):
-        off = 0
-        for p in self.params:
-            yield off
-            off += p.numel()
+    def _flat_grads(self):
+        """The gradients as one flat vector without copying, or None if they are not laid out that way."""
+        g0 = self.params[0].grad
+        if g0 is None:
+            return None
+        es = g0.element_size()
+        st = g0.untyped_storage()
+        base = g0.data_ptr()
+        for p, off in zip(self.params, self._off):
+            g = p.grad
+            if (g is None or g.dtype != g0.dtype or not g.is_contiguous() or g.data_ptr() != base + off * es
+                    or g.untyped_storage().data_ptr() != st.data_ptr()):
+                return None
+        if (g0.storage_offset() + self._opt.n) * es > st.nbytes():
+            return None
+        return g0.as_strided((self._opt.n,), (1,), g0.storage_offset())
 
     def step(self):
-        self._opt.step(self.flat)
+        flat = self._flat_grads()
+        if flat is None:
+            zero = None
+            parts = []
+            for i, p in enumerate(self.params):
+                if p.grad is None:
+                    if zero is None:
+                        zero = torch.zeros(max(q.numel() for q in self.params), dtype=self.flat.dtype, device=self.flat.device)
+                    parts.append(zero[:p.numel()])
+                else:
+                    parts.append(p.grad.reshape(-1))
+            flat = torch.cat(parts)      # (not into self.flat: some of the parts may be views of it)
+            self.gathered_steps += 1
+        else:
+            self.adopted_steps += 1
+        self._opt.step(flat)
 
 
 class FusedTrainer:
@@ -454,8 +503,8 @@ class WanTrainer:
     freshly drawn interior points (``loss_v`` of wan_losses, :244-248), then one solution update on another fresh draw
     with ``w_pde loss_pde_u + w_bc bc + w_data data + w_norm norm`` (:251-271).  The losses are the drop-in operators
     of ``pde_b200.poisson`` (both networks' jets and reverse sweeps on the fused kernels), the optimisers are
-    ``torch.optim.Adam(capturable=True)``, the points come from the device sampler with a draw counter, and the whole
-    epoch is captured into one CUDA graph (``graph=True``).
+    ``pde_b200.train.Adam`` (torch.optim.Adam's arithmetic, one launch per step), the points come from the device
+    sampler with a draw counter, and the whole epoch is captured into one CUDA graph (``graph=True``).
 
     ``record_points=True`` (eager mode only) keeps every draw in ``self.drawn`` = [(kind, X, f) ...] so that a
     reference loop can be run on identical points.
@@ -478,8 +527,8 @@ class WanTrainer:
             self.w.update({k: float(v) for k, v in weights.items()})
         self.norm_mode = norm_mode
         self.seed = int(seed)
-        self.opt_u = torch.optim.Adam(model.parameters(), lr=lr, capturable=bool(graph))
-        self.opt_v = torch.optim.Adam(critic.parameters(), lr=lr, capturable=bool(graph))
+        self.opt_u = Adam(model.parameters(), lr=lr)      # torch.optim.Adam's update, one launch per step
+        self.opt_v = Adam(critic.parameters(), lr=lr)
         self.u_params, self.v_params = list(model.parameters()), list(critic.parameters())
         self.draws = torch.zeros(1, dtype=torch.int64, device=self.dev)
         # static point buffers (one per evaluation of the epoch, so that the autograd graphs of an epoch do not alias)
@@ -519,7 +568,7 @@ class WanTrainer:
         for k in range(self.critic_steps):                                   # Poisson_ND.py:244-248
             X, f = self._draw(self.bufs[k], 'v')
             _, loss_v, _, _ = P.wan_losses(self.model, self.critic, X, f, self.L, v_reg_weight=self.wan_reg)
-            self.opt_v.zero_grad(set_to_none=False)
+            self.opt_v.zero_grad()
             loss_v.backward(inputs=self.v_params)
             self.opt_v.step()
         X, f = self._draw(self.bufs[self.critic_steps], 'u')                 # :251-253
@@ -539,7 +588,7 @@ class WanTrainer:
         if self.w['norm'] > 0.0:                                             # :267-268
             norm_l = P.norm_loss(P.solution_jets(self.model, X.detach(), self.L, 0)[0], mode=self.norm_mode)
         loss = self.w['pde'] * loss_pde_u + self.w['bc'] * bc_l + self.w['data'] * data_l + self.w['norm'] * norm_l
-        self.opt_u.zero_grad(set_to_none=False)
+        self.opt_u.zero_grad()
         loss.backward(inputs=self.u_params)
         self.opt_u.step()
         return {'total': loss.detach(), 'pde': loss_pde_u.detach(), 'bc': bc_l.detach(), 'data': data_l.detach(),

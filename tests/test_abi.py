@@ -99,3 +99,92 @@ def test_host_side_settings():
     # invalid arguments are refused before anything is enqueued
     assert lib.pde_wan_scalars(L.F32, 5, None, None, None, None, None) == -1
     assert lib.pde_residual_loss_grad_exchange(None, None, None, None, 0, None, 1.0, None, None, 0, None, 0, None, None) == -1
+
+
+def test_train_adam_takes_adopted_gradients_without_copy(monkeypatch):
+    """Host logic of pb.train.Adam (the launch itself needs a GPU and is covered by tests/test_gpu_train.py): after
+    zero_grad() autograd adopts the views of one flat gradient buffer that the drop-in operators return, and step()
+    hands that buffer to the kernel as it is; any other layout is gathered; set_to_none=False keeps the optimiser's
+    own views."""
+    import torch
+    from pde_b200 import train as T
+
+    seen = []
+
+    class Recorder:           # stands in for FusedAdam (which insists on CUDA tensors)
+        def __init__(self, params, **kw):
+            self.n = sum(p.numel() for p in params)
+            self.exp_avg = self.exp_avg_sq = self.step_count = None
+
+        def step(self, flat, grad_scale=1.0):
+            seen.append(flat)
+
+    monkeypatch.setattr(T, "FusedAdam", Recorder)
+
+    class FlatGrad(torch.autograd.Function):      # the shape of ops._Residual.backward / ops._Jets.backward
+        @staticmethod
+        def forward(ctx, *ps):
+            ctx.shapes = [p.shape for p in ps]
+            return sum((p * p).sum() for p in ps).detach() * 0.5
+
+        @staticmethod
+        def backward(ctx, g):
+            n = sum(s.numel() for s in ctx.shapes)
+            flat = torch.arange(1, n + 1, dtype=torch.float64) * g
+            FlatGrad.last = flat
+            out, o = [], 0
+            for s in ctx.shapes:
+                out.append(flat[o:o + s.numel()].view(s)); o += s.numel()
+            return tuple(out)
+
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(3, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1)).double()
+    ps = list(m.parameters())
+    n = sum(p.numel() for p in ps)
+    want = torch.arange(1, n + 1, dtype=torch.float64)
+    opt = T.Adam(ps, lr=1e-3)
+
+    # adopted: no copy, the kernel would read the operator's own buffer
+    opt.zero_grad()
+    FlatGrad.apply(*ps).backward()
+    opt.step()
+    assert opt.adopted_steps == 1 and opt.gathered_steps == 0
+    assert seen[-1].data_ptr() == FlatGrad.last.data_ptr() and torch.equal(seen[-1], want)
+    # a second backward() accumulates into the adopted views in place: layout kept
+    opt.zero_grad()
+    FlatGrad.apply(*ps).backward()
+    (2.0 * FlatGrad.apply(*ps)).backward()
+    opt.step()
+    assert opt.adopted_steps == 2 and opt.gathered_steps == 0 and torch.equal(seen[-1], 3.0 * want)
+    # two terms in one backward(): the engine sums them per parameter before they reach p.grad -> gathered, same values
+    opt.zero_grad()
+    (FlatGrad.apply(*ps) + 2.0 * FlatGrad.apply(*ps)).backward()
+    opt.step()
+    assert opt.adopted_steps == 2 and opt.gathered_steps == 1 and torch.equal(seen[-1], 3.0 * want)
+    opt.gathered_steps = 0
+    # gradients of ordinary torch operators: gathered, same values as torch.cat
+    opt.zero_grad()
+    m(torch.ones(5, 3, dtype=torch.float64)).sum().backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in ps])
+    opt.step()
+    assert opt.gathered_steps == 1 and torch.equal(seen[-1], ref)
+    # a parameter without gradient counts as zero; a subset (backward(inputs=...)) is gathered
+    opt.zero_grad()
+    FlatGrad.apply(*ps).backward(inputs=ps[:2])
+    opt.step()
+    k = ps[0].numel() + ps[1].numel()
+    assert opt.gathered_steps == 2 and torch.equal(seen[-1][:k], want[:k]) and not seen[-1][k:].any()
+    # set_to_none=False: the optimiser's own views, zeroed by one fill, accumulated into by autograd
+    opt.zero_grad(set_to_none=False)
+    assert all(p.grad.data_ptr() == opt.flat.data_ptr() + off * 8 for p, off in zip(ps, opt._off))
+    FlatGrad.apply(*ps).backward()
+    opt.step()
+    assert seen[-1].data_ptr() == opt.flat.data_ptr() and torch.equal(seen[-1], want)
+    opt.zero_grad(set_to_none=False)
+    assert not opt.flat.any() and all(p.grad.data_ptr() == opt.flat.data_ptr() + off * 8 for p, off in zip(ps, opt._off))
+    # a different parameter order than the operator's: not consecutive, hence gathered — never misread
+    opt2 = T.Adam(ps[::-1], lr=1e-3)
+    opt2.zero_grad()
+    FlatGrad.apply(*ps).backward()
+    opt2.step()
+    assert opt2.gathered_steps == 1 and torch.equal(seen[-1], torch.cat([p.grad.reshape(-1) for p in ps[::-1]]))

@@ -179,9 +179,12 @@ def test_wan_frozen_jets_give_identical_losses_and_grads():
 
 
 @pytest.mark.parametrize("graph", [False, True])
-def test_train_adam_dropin_matches_torch_adam(graph):
-    """pb.train.Adam (gradients as views of one flat buffer, one pde_adam_step launch per step) follows
-    torch.optim.Adam through a reference-style epoch on the QHO 2-D PINN loss, eagerly and as a replayed CUDA graph."""
+@pytest.mark.parametrize("set_to_none", [False, True])
+def test_train_adam_dropin_matches_torch_adam(graph, set_to_none):
+    """pb.train.Adam (one flat gradient vector, one pde_adam_step launch per step) follows torch.optim.Adam through a
+    reference-style epoch on the QHO 2-D PINN loss, eagerly and as a replayed CUDA graph — with the gradients adopted
+    from the loss operator's own buffer (zero_grad(): no fill, no per-parameter accumulation) and with the optimiser's
+    own views (set_to_none=False)."""
     from pde_b200.schrodinger import qho_2d as Q
     g1 = torch.linspace(-6.0, 6.0, 40, dtype=torch.float64)
     xg, yg = torch.meshgrid(g1, g1, indexing="ij")
@@ -196,16 +199,16 @@ def test_train_adam_dropin_matches_torch_adam(graph):
                                                                                       #  the bias corrections, in float32: 6e-6 off per step)
 
         def epoch():
-            opt.zero_grad(set_to_none=False)
+            opt.zero_grad(set_to_none=set_to_none)
             l = Q.PINN_loss(m, xd, yd, E, 6.0)
             l.backward()
             opt.step()
             return l.detach()
-        return m, epoch
-    m_ref, ep_ref = build("torch")
+        return m, epoch, opt
+    m_ref, ep_ref, _ = build("torch")
     for _ in range(7):
         l_ref = ep_ref()
-    m_new, ep_new = build("fused")
+    m_new, ep_new, opt_new = build("fused")
     if graph:
         ge = pb.train.GraphedEpoch(ep_new, warmup=3)
         ge()                       # 3 eager epochs + capture
@@ -218,6 +221,8 @@ def test_train_adam_dropin_matches_torch_adam(graph):
     assert abs(float(l_new) - float(l_ref)) <= 1e-9 * abs(float(l_ref))
     for a, b in zip(m_new.parameters(), m_ref.parameters()):
         assert float((a - b).abs().max()) <= 1e-9 * max(1.0, float(b.abs().max()))
+    # every step read the gradients where they were (the operator's buffer or the optimiser's own): nothing gathered
+    assert opt_new.gathered_steps == 0 and opt_new.adopted_steps == (4 if graph else 7)
 
 
 def test_graphed_wan_epoch_matches_eager():
