@@ -596,7 +596,10 @@ def wan_means(u_model, v_model, X, spec: WanSpec, env_u=NO_ENVELOPE, env_v=NO_EN
     def coef(t):
         if t is None:
             return None
-        return t.detach().to(X.dtype).reshape(-1).contiguous()
+        t = t.detach().to(X.dtype).reshape(-1).contiguous()
+        if t.numel() != n or t.device != X.device:
+            raise ValueError("per-point coefficient must have one value per point on the points' device")
+        return t
 
     e = None
     if energy is not None:
