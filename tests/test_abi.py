@@ -188,3 +188,59 @@ def test_train_adam_takes_adopted_gradients_without_copy(monkeypatch):
     FlatGrad.apply(*ps).backward()
     opt2.step()
     assert opt2.gathered_steps == 1 and torch.equal(seen[-1], torch.cat([p.grad.reshape(-1) for p in ps[::-1]]))
+
+
+def test_linear_stack_reads_every_reference_module_layout():
+    """ops._linear_stack finds the Linear layers and the activation in each layout the reference's scripts use
+    (Sequential under .net; UnifiedEigenModel.u_model.net; FCN_Single.net -> FCN.layers ModuleList with the
+    activation as an attribute; a bare Sequential) and refuses what the kernels do not implement."""
+    import torch
+    import torch.nn as nn
+    from pde_b200 import ops
+    from pde_b200.schrodinger import ipw_1d_wan, kh_1d, qho_1d_pinn_drm, qho_2d
+
+    def widths(lin):
+        return [lin[0].in_features] + [m.out_features for m in lin]
+
+    lin, act = ops._linear_stack(pb.poisson.SolutionNet(3, 64, 5, "FBC"))
+    assert widths(lin) == [3, 64, 64, 64, 64, 1] and act == "sin"
+    lin, act = ops._linear_stack(pb.poisson.CriticNet(2, 16, 3))
+    assert widths(lin) == [2, 16, 16, 1] and act == "sin"
+    lin, act = ops._linear_stack(ipw_1d_wan.FCN([1, 50, 50, 50, 1], L=2.0, enforce_bc=True))
+    assert widths(lin) == [1, 50, 50, 50, 1] and act == "tanh"
+    lin, act = ops._linear_stack(qho_2d.FCN([2, 50, 50, 50, 50, 1], 2, 1, "FN"))
+    assert widths(lin) == [2, 50, 50, 50, 50, 1] and act == "sin"
+    um = kh_1d.UnifiedEigenModel([1, 100, 100, 100, 1], "FBC", 60.0)
+    lin, act = ops._linear_stack(um)
+    assert widths(lin) == [1, 100, 100, 100, 1] and lin[0] is um.u_model.net[0]
+    single = qho_1d_pinn_drm.FCN_Single([1, 20, 20, 1], num_states=1)
+    lin, act = ops._linear_stack(single)
+    assert widths(lin) == [1, 20, 20, 1] and act in ("tanh", "sin")
+    lin, act = ops._linear_stack(nn.Sequential(nn.Linear(2, 8), nn.Tanh(), nn.Linear(8, 1)))
+    assert widths(lin) == [2, 8, 1] and act == "tanh"
+    # the parameter order the kernels' flat gradient uses is nn.Module.parameters() order
+    m = pb.poisson.SolutionNet(2, 8, 3, "RB")
+    lin, _ = ops._linear_stack(m)
+    assert [id(p) for l in lin for p in (l.weight, l.bias)] == [id(p) for p in m.parameters()]
+    with pytest.raises(NotImplementedError):
+        ops._linear_stack(nn.Sequential(nn.Linear(2, 8), nn.ReLU(), nn.Linear(8, 1)))
+    with pytest.raises(NotImplementedError):
+        ops._linear_stack(nn.Sequential(nn.Linear(2, 8), nn.Tanh(), nn.Linear(8, 8), pb.poisson.Sin(), nn.Linear(8, 1)))
+    with pytest.raises(ValueError):
+        ops._linear_stack(nn.Sequential(nn.Tanh()))
+    # points on the CPU: refused loudly, never computed some other way
+    with pytest.raises(L.PdeError):
+        ops._Net(m, torch.zeros(4, 2))
+
+
+def test_envelope_struct_cache_follows_the_description():
+    """EnvelopeSpec.to_c caches the ctypes struct per description and rebuilds it when a field changes."""
+    from pde_b200.ops import EnvelopeSpec
+    e = EnvelopeSpec(L.ENV_POLY, 0.0, 2.0, [[0.5, 1.5]])
+    c1 = e.to_c()
+    assert e.to_c() is c1 and c1.kind == L.ENV_POLY and c1.hi == 2.0 and c1.n_nodes[0] == 2 and c1.nodes[0][1] == 1.5
+    e.hi = 3.0
+    c2 = e.to_c()
+    assert c2 is not c1 and c2.hi == 3.0 and e.to_c() is c2
+    with pytest.raises(NotImplementedError):
+        EnvelopeSpec(L.ENV_POLY, 0.0, 2.0, [[0.1 * k for k in range(L.MAX_NODES + 1)]]).to_c()
