@@ -221,13 +221,31 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_unflatten = getattr(torch._C._nn, "unflatten_dense_tensors", None)
+
+
 def _split_flat(flat, params):
+    """Views of ``flat`` shaped like ``params``, in order (one native call where torch has it)."""
+    if _unflatten is not None:
+        return list(_unflatten(flat, params))
     out, o = [], 0
     for p in params:
         k = p.numel()
         out.append(flat[o:o + k].view_as(p))
         o += k
     return out
+
+
+_PROG_INFO = {}
+
+
+def _program_info(kind):
+    """(number of quantities, derivative order) of a residual program (pure library queries, cached)."""
+    info = _PROG_INFO.get(kind)
+    if info is None:
+        lib = L.load()
+        info = _PROG_INFO[kind] = (lib.pde_program_quantities(kind), lib.pde_program_order(kind))
+    return info
 
 
 def _points(X):
@@ -357,8 +375,7 @@ class _Residual(torch.autograd.Function):
         ps = [p.detach().contiguous() for p in params]
         cnet = net.to_c(ps)
         n = X.shape[0]
-        K = lib.pde_program_quantities(spec.kind)
-        order = lib.pde_program_order(spec.kind)
+        K, order = _program_info(spec.kind)
         dev, dt = X.device, X.dtype
         nparam = sum(p.numel() for p in ps)
         n_tot = float(n if n_global is None else n_global)
@@ -395,7 +412,7 @@ class _Residual(torch.autograd.Function):
         ctx.has_energy = energy is not None
         if fused:
             ctx.save_for_backward(buf)
-            ctx.shapes = [p.shape for p in ps]
+            ctx.ps = ps
         else:
             ctx.save_for_backward(X, f, beta, e_dev, *ps)
         return means     # (a fresh tensor: the division in combine_forward)
@@ -407,14 +424,9 @@ class _Residual(torch.autograd.Function):
         if ctx.fused:
             (buf,) = ctx.saved_tensors
             nparam = buf.numel() - 1 - ctx.K
-            flat = buf[:nparam] * gmeans[0]
+            flat = buf[:nparam] * gmeans          # (K = 1: gmeans has one element)
             gE = (buf[nparam] * gmeans[0]) if ctx.has_energy else None
-            grads, o = [], 0
-            for shp in ctx.shapes:
-                k = 1
-                for s in shp:
-                    k *= s
-                grads.append(flat[o:o + k].view(shp)); o += k
+            grads = _split_flat(flat, ctx.ps)
         else:
             lib = L.load()
             X, f, beta, e_dev, *ps = ctx.saved_tensors
@@ -429,7 +441,7 @@ class _Residual(torch.autograd.Function):
             prog.beta = beta.data_ptr() if beta is not None else None
             prog.energy = e_dev.data_ptr() if e_dev is not None else None
             cenv = env.to_c()
-            order = lib.pde_program_order(spec.kind)
+            order = _program_info(spec.kind)[1]
             seed = gmeans.detach().to(dt).contiguous()
             ws = _ws_for(cnet, order, n, dev)
             with torch.cuda.device(dev):
@@ -470,7 +482,12 @@ def residual_means(model, X, spec: ProgramSpec, env: EnvelopeSpec = NO_ENVELOPE,
     def coef(t):
         if t is None:
             return None
-        t = t.detach().to(X.dtype).reshape(-1).contiguous()
+        t = t.detach()
+        if t.dtype != X.dtype:
+            t = t.to(X.dtype)
+        t = t.reshape(-1)
+        if not t.is_contiguous():
+            t = t.contiguous()
         if t.numel() != n or t.device != X.device:
             raise ValueError("per-point coefficient must have one value per point on the points' device")
         return t
